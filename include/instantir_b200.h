@@ -1,0 +1,189 @@
+/*
+ * instantir_b200.h — C ABI of the B200-native InstantIR denoising-step kernels.
+ *
+ * The reference (rebots-online/InstantIR) has no FFI layer: its hot path is Python calling
+ * torch ops (cuDNN conv, cuBLAS GEMM, SDPA, native norms).  Each entry point below replaces the
+ * torch op(s) named in its comment, cited as reference file:line.  The Python host
+ * (instantir_b200/*.py) binds these through ctypes; see INTEGRATION.md for the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch); the library never frees it
+ *   - activations are NHWC / token-major: a [B,C,H,W] reference tensor is stored as [B*H*W, C]
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success, negative iir_status on failure; iir_last_error() gives the text
+ *   - no exceptions cross the boundary; no CPU fallback exists: without a CUDA device every
+ *     compute entry point returns IIR_ERR_CUDA
+ */
+#ifndef INSTANTIR_B200_H
+#define INSTANTIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIR_ABI_VERSION 1
+
+typedef enum {
+  IIR_OK = 0,
+  IIR_ERR_INVALID = -1,     /* bad argument (shape, alignment, dtype) */
+  IIR_ERR_CUDA = -2,        /* CUDA runtime / driver error             */
+  IIR_ERR_UNSUPPORTED = -3  /* shape outside what the sm_100a kernel handles */
+} iir_status;
+
+typedef enum { IIR_F32 = 0, IIR_BF16 = 1 } iir_dtype;
+typedef enum { IIR_ACT_NONE = 0, IIR_ACT_SILU = 1, IIR_ACT_GELU = 2 } iir_act;
+/* paired epilogues: weight rows are packed per `bn`-wide tile as [first half | second half]
+ *   GEGLU: out = (x1 + b1) * gelu_erf(x2 + b2)      reference module/min_sdxl.py:502-510
+ *   SFT  : out = h * (gamma + 1) + beta             reference module/aggregator.py:70-90   */
+typedef enum { IIR_PAIR_NONE = 0, IIR_PAIR_GEGLU = 1, IIR_PAIR_SFT = 2 } iir_pair;
+
+int iir_abi_version(void);
+const char* iir_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
+uint64_t iir_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution:  out = epilogue( A · Wᵀ )
+ * Replaces nn.Linear (module/min_sdxl.py:301-307,505-523,569-573) and nn.Conv2d 3x3/1x1
+ * (module/min_sdxl.py:246-260,601-618; module/aggregator.py:63-68) + the elementwise ops the
+ * reference runs after them (bias, temb add :269-270, residual add :281, GEGLU, SFT).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a;        /* linear: [M, K] row-major, leading dim lda (elements)
+                           conv  : NHWC [n_img, H, W, Cin]                              */
+  const void* w;        /* [N, K] row-major (K = taps*Cin, tap-major: k = (ky*3+kx)*Cin + c) */
+  int a_dtype;          /* tc: must be IIR_BF16; simt: F32 or BF16                        */
+  int w_dtype;
+  int M, N, K;          /* conv: M = n_img*Ho*Wo                                          */
+  int64_t lda;
+  int conv;             /* 0 = linear, 3 = 3x3 pad 1                                      */
+  int n_img, H, W, Cin; /* conv input geometry (H,W = input size AFTER optional upsample) */
+  int stride;           /* conv stride 1 or 2 (tc: 1 only)                                */
+  int up2;              /* simt only: input is nearest-2x upsampled on the fly            */
+  const float* bias;    /* [N] or NULL (packed order for paired epilogues)                */
+  const float* rowvec;  /* [n_samples, N] added to every row of a sample, or NULL         */
+  int rows_per_sample;
+  const void* residual; /* [M, N_out] added last, or NULL                                 */
+  int res_dtype; int64_t ld_res;
+  const void* aux;      /* SFT: h [M, N_out]                                              */
+  int aux_dtype; int64_t ld_aux;
+  void* out;            /* [M, N_out], N_out = N (or N/2 for paired epilogues)            */
+  int out_dtype; int64_t ld_out;
+  int act;              /* iir_act applied to (acc + bias + rowvec)                       */
+  int pair;             /* iir_pair                                                       */
+  int bn;               /* N tile (multiple of 32, <=256; multiple of 64 when paired)     */
+} iir_gemm_args;
+
+/* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */
+int iir_gemm_tc(const iir_gemm_args* args, void* stream);
+/* fp32 SIMT kernel: the "fp32 check mode" of the north star and the on-GPU cross-check */
+int iir_gemm_simt(const iir_gemm_args* args, void* stream);
+
+/* Direct convolution for tiny channel counts (conv_in 4->C, conv_out C->4):
+ * module/min_sdxl.py:803,840; module/aggregator.py:304-306,394-396.
+ * in : NCHW (in_nchw=1) or NHWC;  out: NHWC rows [out_row_off + y] of an image of out_H rows
+ * (lets the Aggregator write both halves of its 2h x w canvas, module/aggregator.py:889-902),
+ * or NCHW when out_nchw=1.  w: [Cout, 3, 3, Cin] fp32, bias [Cout] fp32.                  */
+int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, const float* w, const float* bias,
+                       void* out, int out_dtype, int out_nchw, int n_img, int H, int W, int Cin,
+                       int Cout, int out_H, int out_row_off, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention: softmax(Q Kᵀ * scale) V per head (head_dim 64), up to two independent key
+ * segments summed with per-segment weights:
+ *   out = seg_scale[0]*SDPA(Q,K0,V0) + seg_scale[1]*SDPA(Q,K1,V1)
+ * One segment  = AttnProcessor2_0   (module/ip_adapter/attention_processor.py:394-396)
+ * Two segments = TA_IPAttnProcessor2_0 text + image (same file :1165-1192)
+ * Q/K/V/out are [B, n, ld] row-major bf16 (tc) with head h at column off + 64*h.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q; int64_t ldq; int q_off;
+  int n_seg;
+  const void* k[2]; int64_t ldk[2]; int k_off[2];
+  const void* v[2]; int64_t ldv[2]; int v_off[2];
+  int kv_len[2];
+  float seg_scale[2];
+  void* out; int64_t ldo; int out_off;
+  int dtype;            /* IIR_BF16 (tc) or IIR_F32/IIR_BF16 (simt), all tensors           */
+  int B, heads, n_q;
+  float softmax_scale;  /* 1/sqrt(64) (Resampler: also 1/8 = (64^-1/4)^2, resampler.py:71-72) */
+} iir_attn_args;
+
+int iir_attn_tc(const iir_attn_args* args, void* stream);
+int iir_attn_simt(const iir_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalisation
+ * ---------------------------------------------------------------------------------------- */
+/* GroupNorm(32 groups) [+ SiLU] over NHWC x [n_img, HW, C]: module/min_sdxl.py:245,250,568,838.
+ * `partials` is caller-owned scratch of iir_groupnorm_scratch_floats(...) floats.          */
+int64_t iir_groupnorm_scratch_floats(int n_img, int groups);
+int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* out,
+                  int out_dtype, int n_img, int HW, int C, int groups, float eps, int silu,
+                  float* partials, void* stream);
+/* LayerNorm over the last dim, optional affine (gamma/beta) and optional adaLN modulation
+ * out = LN(x) * (1 + mod[b, C:2C]) + mod[b, 0:C]  (module/ip_adapter/attention_processor.py:18-26;
+ * module/min_sdxl.py:534-538).                                                              */
+int iir_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta,
+                  const float* mod, int rows_per_sample, void* out, int out_dtype, int rows, int C,
+                  float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data movement fused with the reference's elementwise steps
+ * ---------------------------------------------------------------------------------------- */
+/* out[M, C1+C2] = cat( h (+ s[b]*rh), skip (+ s[b]*rs) ) along channels:
+ * torch.cat of the up blocks (module/min_sdxl.py:708,745) fused with the ControlNet residual
+ * injection skip_i + cond_scale*res_i (pipelines/sdxl_instantir.py:1602-1603).
+ * C2 may be 0 (plain scaled add).                                                           */
+int iir_concat_inject(const void* h, int h_dtype, int C1, const void* rh, int rh_dtype,
+                      const void* skip, int skip_dtype, int C2, const void* rs, int rs_dtype,
+                      const float* cond_scale, int rows_per_sample, void* out, int out_dtype,
+                      int64_t M, void* stream);
+/* nearest 2x upsample NHWC (module/min_sdxl.py:617) with dtype conversion                   */
+int iir_upsample2x(const void* x, int x_dtype, void* out, int out_dtype, int n_img, int H, int W,
+                   int C, void* stream);
+/* 3x3 stride-2 pad-1 patch gather -> [n_img*Ho*Wo, 9*C] (Downsample2D, module/min_sdxl.py:598-606) */
+int iir_im2col3x3_s2(const void* x, int x_dtype, void* out, int out_dtype, int n_img, int H, int W,
+                     int C, void* stream);
+/* strided 2-D copy/cast: out[r, c] = in[r*ld_in + c]                                        */
+int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
+               int64_t ld_out, int64_t rows, int cols, void* stream);
+/* out = silu(x) elementwise (temb nonlinearity, module/min_sdxl.py:268)                     */
+int iir_silu(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, void* stream);
+/* out = a + b                                                                               */
+int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, void* out, int out_dtype,
+            int64_t n, void* stream);
+
+/* sinusoidal timestep embedding [cos|sin], flip_sin_to_cos=True, freq_shift=0
+ * (module/min_sdxl.py:205-224): t [n] fp32 -> out [n, dim]                                  */
+int iir_timestep_embedding(const float* t, int n, int dim, void* out, int out_dtype, void* stream);
+/* small-M linear (M <= 16): time/add embedding MLPs, time_emb_proj, adaLN linears
+ * (module/min_sdxl.py:227-239,249; attention_processor.py:14,23). w [N,K] F32/BF16          */
+int iir_linear_small(const void* x, int x_dtype, const void* w, int w_dtype, const float* bias,
+                     void* out, int out_dtype, int M, int N, int K, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scheduler / guidance kernels (fp32 latents, NCHW [B,4,h,w] flattened)
+ * ---------------------------------------------------------------------------------------- */
+/* LCM single-step preview: schedulers/lcm_single_step_scheduler.py:421-489
+ *   x0 = (x - sqrt(1-abar) eps)/sqrt(abar);  out = c_out*x0 + c_skip*x                      */
+int iir_lcm_step(const void* eps, int eps_dtype, const float* x, float* out, int64_t n,
+                 float alpha_prod_t, float c_skip, float c_out, void* stream);
+/* CFG combine (pipelines/sdxl_instantir.py:1619-1621) + DDPM ancestral step (diffusers
+ * DDPMScheduler.step):
+ *   eps = eps_u + g (eps_c - eps_u); x0 = (x - sqrt(1-abar_t) eps)/sqrt(abar_t)
+ *   prev = c_x0*x0 + c_xt*x + sigma*noise                                                   */
+int iir_cfg_ddpm_step(const void* eps_uncond, const void* eps_cond, int eps_dtype, const float* x,
+                      const float* noise, float* prev, float* pred_x0, int64_t n, float guidance,
+                      float alpha_prod_t, float c_x0, float c_xt, float sigma, void* stream);
+/* add_noise (lcm_single_step_scheduler.py:492-513): out = sqrt(abar)*x0 + sqrt(1-abar)*noise */
+int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n, float alpha_prod_t,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTANTIR_B200_H */

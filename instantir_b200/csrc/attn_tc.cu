@@ -1,0 +1,357 @@
+// Flash-style attention on tcgen05 / TMEM for sm_100a, head_dim 64, bf16.
+//
+//   out = sum_s seg_scale[s] * softmax(Q K_sᵀ * scale) V_s         (1 or 2 key segments)
+//
+// One CTA per (128-query tile, head, batch):
+//   warp 0     : TMA producer — Q once, then (K_j, V_j) 128-key blocks, double buffered
+//   warp 1     : single-thread MMA issuer.  S_j = Q K_jᵀ (UMMA 128x128x16 x4) into one of two
+//                TMEM S buffers; O_j = P_j V_j (UMMA 128x64x16 x8, V as MN-major B operand) into one
+//                of two TMEM O buffers.  S_{j+1} is issued before P_j V_j so the tensor core works
+//                while the softmax warps are busy with block j.
+//   warps 2..5 : softmax — one query row per thread (TMEM lane == row, no shuffles): row max,
+//                exp2, row sum, P_j -> bf16 into 128B-swizzled smem (A operand of the PV MMA),
+//                then o = o*alpha + O_j read back from TMEM (accumulator kept in registers).
+// Two segments = decoupled text + image cross-attention with independent softmaxes
+// (module/ip_adapter/attention_processor.py:1165-1192); one segment = self-attention (:394-396).
+#include "common.cuh"
+
+namespace iir {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int ATT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KiB: Q, K_j, V_j tiles; P_j is two of these
+
+struct alignas(64) AttnTcParams {
+  CUtensorMap tmQ;
+  CUtensorMap tmK[2];
+  CUtensorMap tmV[2];
+  int n_seg;
+  int kv_len[2];
+  int nblk[2];
+  float seg_scale[2];
+  int q_off, k_off[2], v_off[2];
+  bf16* out;
+  long long ldo;
+  int out_off;
+  int B, heads, n_q;
+  float scale_log2;  // softmax_scale * log2(e)
+};
+
+template <int NSEG>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
+  uint8_t* sP = sV + 2 * TILE_BYTES;   // 2 buffers x 32 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // 2
+  uint64_t* kv_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* s_empty = bars + 7;       // 2
+  uint64_t* p_full = bars + 9;        // 2
+  uint64_t* p_empty = bars + 11;      // 2
+  uint64_t* o_full = bars + 13;       // 2
+  uint64_t* o_empty = bars + 15;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nb_total = p.nblk[0] + (NSEG > 1 ? p.nblk[1] : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK[0]);
+    tma_prefetch_desc(&p.tmV[0]);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&p_empty[s], 1);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_empty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
+  const uint32_t tmem_O = tmem_base + 256;  // 2 x 64 columns
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
+      int jb = 0;
+      for (int s = 0; s < NSEG; ++s) {
+        for (int jl = 0; jl < p.nblk[s]; ++jl, ++jb) {
+          const int st = jb & 1;
+          const uint32_t ph = (jb >> 1) & 1;
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          tma_load_3d(sK + st * TILE_BYTES, &p.tmK[s], &kv_full[st], p.k_off[s] + h * 64, jl * 128, b);
+          tma_load_3d(sV + st * TILE_BYTES, &p.tmV[s], &kv_full[st], p.v_off[s] + h * 64, jl * 128, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      auto issue_pv = [&](int j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&p_full[st], ph);
+        mbar_wait(&o_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + st * 2 * TILE_BYTES);
+        const uint32_t va = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint64_t adesc = umma_desc_sw128(pa + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
+          uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
+          umma_bf16(tmem_O + st * 64, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_empty[st]);
+        umma_commit(&o_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      const uint32_t qa = smem_u32(sQ);
+      for (int jb = 0; jb < nb_total; ++jb) {
+        const int st = jb & 1;
+        const uint32_t ph = (jb >> 1) & 1;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t adesc = umma_desc_sw128(qa + k * 32, 16, 1024);
+          uint64_t bdesc = umma_desc_sw128(ka + k * 32, 16, 1024);
+          umma_bf16(tmem_S + st * 128, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+        if (jb > 0) issue_pv(jb - 1);
+      }
+      issue_pv(nb_total - 1);
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    const uint32_t trow = static_cast<uint32_t>(lane_base) << 16;
+    const float sl2 = p.scale_log2;
+    float out_acc[64];
+    if (NSEG > 1) {
+#pragma unroll
+      for (int d = 0; d < 64; ++d) out_acc[d] = 0.f;
+    }
+    float o_acc[64];
+    int jb = 0;
+#pragma unroll 1
+    for (int s = 0; s < NSEG; ++s) {
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o_acc[d] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      const int seg_first = jb;
+
+      auto consume_o = [&](int j, float alpha) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&o_full[st], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(tmem_O + trow + st * 64 + half * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 32; ++d)
+            o_acc[half * 32 + d] = fmaf(o_acc[half * 32 + d], alpha, __uint_as_float(r[d]));
+        }
+        tc_fence_before();
+        mbar_arrive(&o_empty[st]);
+      };
+
+#pragma unroll 1
+      for (int jl = 0; jl < p.nblk[s]; ++jl, ++jb) {
+        const int st = jb & 1;
+        const uint32_t ph = (jb >> 1) & 1;
+        const int valid = min(128, p.kv_len[s] - jl * 128);
+        mbar_wait(&s_full[st], ph);
+        tc_fence_after();
+        const uint32_t ts = tmem_S + trow + st * 128;
+        // pass 1: row max
+        float mx = m_run;
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(ts + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        const float alpha = exp2f((m_run - mx) * sl2);
+        const float mneg = -mx * sl2;
+        // pass 2: P = exp2(S*sl2 - m*sl2) -> bf16 smem (swizzled K-major A operand), row sum
+        mbar_wait(&p_empty[st], ph ^ 1);
+        uint8_t* prow = sP + st * 2 * TILE_BYTES + row * 128;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(ts + cc, r);
+          tmem_ld_wait();
+          float pv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = exp2f(fmaf(__uint_as_float(r[j]), sl2, mneg));
+            pv[j] = (cc + j < valid) ? e : 0.f;
+            sum += pv[j];
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = cc + g * 8;          // first key column of this 16-byte chunk
+            const int panel = c >> 6;
+            const int q8 = (c & 63) >> 3;
+            uint4 u;
+            u.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]);
+            u.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
+            u.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]);
+            u.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + panel * TILE_BYTES + ((q8 ^ (row & 7)) << 4)) = u;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[st]);
+        fence_async_smem();
+        mbar_arrive(&p_full[st]);
+        l_run = l_run * alpha + sum;
+        m_run = mx;
+        if (jb > seg_first) consume_o(jb - 1, alpha_prev);
+        alpha_prev = alpha;
+      }
+      consume_o(jb - 1, alpha_prev);
+      const float w = p.seg_scale[s] / l_run;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int d = 0; d < 64; ++d) out_acc[d] = fmaf(o_acc[d], w, out_acc[d]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o_acc[d] *= w;
+      }
+    }
+    const int qi = q0 + row;
+    if (qi < p.n_q) {
+      bf16* o = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
+#pragma unroll
+      for (int d = 0; d < 64; d += 8) {
+        uint4 u;
+        if (NSEG > 1) {
+          u.x = pack_bf16(out_acc[d], out_acc[d + 1]);
+          u.y = pack_bf16(out_acc[d + 2], out_acc[d + 3]);
+          u.z = pack_bf16(out_acc[d + 4], out_acc[d + 5]);
+          u.w = pack_bf16(out_acc[d + 6], out_acc[d + 7]);
+        } else {
+          u.x = pack_bf16(o_acc[d], o_acc[d + 1]);
+          u.y = pack_bf16(o_acc[d + 2], o_acc[d + 3]);
+          u.z = pack_bf16(o_acc[d + 4], o_acc[d + 5]);
+          u.w = pack_bf16(o_acc[d + 6], o_acc[d + 7]);
+        }
+        *reinterpret_cast<uint4*>(o + d) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int B) {
+  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)rows * ld * 2};
+  uint32_t box[3] = {64, 128, 1};
+  CUresult cr = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+  if (cr != CUDA_SUCCESS) {
+    set_error("iir_attn_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return IIR_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace iir
+
+extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
+  using namespace iir;
+  IIR_REQUIRE(a != nullptr, "iir_attn_tc: null args");
+  IIR_REQUIRE(a->dtype == IIR_BF16, "iir_attn_tc: bf16 only (use iir_attn_simt for fp32)");
+  IIR_REQUIRE(a->n_seg == 1 || a->n_seg == 2, "iir_attn_tc: n_seg must be 1 or 2");
+  IIR_REQUIRE(a->B > 0 && a->heads > 0 && a->n_q > 0, "iir_attn_tc: empty problem");
+  IIR_REQUIRE(a->ldq % 8 == 0 && a->ldo % 8 == 0 && a->q_off % 8 == 0 && a->out_off % 8 == 0,
+              "iir_attn_tc: leading dims / offsets must be multiples of 8");
+  AttnTcParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_map3(&p.tmQ, a->q, a->ldq, a->n_q, a->B);
+  if (rc) return rc;
+  p.n_seg = a->n_seg;
+  for (int s = 0; s < a->n_seg; ++s) {
+    IIR_REQUIRE(a->kv_len[s] > 0, "iir_attn_tc: empty key segment %d", s);
+    IIR_REQUIRE(a->ldk[s] % 8 == 0 && a->ldv[s] % 8 == 0 && a->k_off[s] % 8 == 0 && a->v_off[s] % 8 == 0,
+                "iir_attn_tc: K/V leading dims / offsets must be multiples of 8");
+    rc = make_map3(&p.tmK[s], a->k[s], a->ldk[s], a->kv_len[s], a->B);
+    if (rc) return rc;
+    rc = make_map3(&p.tmV[s], a->v[s], a->ldv[s], a->kv_len[s], a->B);
+    if (rc) return rc;
+    p.kv_len[s] = a->kv_len[s];
+    p.nblk[s] = (a->kv_len[s] + 127) / 128;
+    p.seg_scale[s] = a->seg_scale[s];
+    p.k_off[s] = a->k_off[s];
+    p.v_off[s] = a->v_off[s];
+  }
+  p.q_off = a->q_off;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.ldo = a->ldo;
+  p.out_off = a->out_off;
+  p.B = a->B; p.heads = a->heads; p.n_q = a->n_q;
+  p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+
+  const size_t smem = 9 * TILE_BYTES + 1024 + 256;
+  dim3 grid((a->n_q + 127) / 128, a->heads, a->B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (a->n_seg == 1) {
+    e = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) attn_tc_kernel<1><<<grid, ATT_THREADS, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) attn_tc_kernel<2><<<grid, ATT_THREADS, smem, st>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("iir_attn_tc: %s", cudaGetErrorString(e));
+    return IIR_ERR_CUDA;
+  }
+  count_launch();
+  return check_launch("iir_attn_tc");
+}

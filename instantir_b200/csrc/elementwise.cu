@@ -1,0 +1,219 @@
+// Data-movement kernels fused with the reference's elementwise steps (HBM-bound, vectorised).
+#include "common.cuh"
+
+namespace iir {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float4 ld4_any(const void* p, int is_bf16, long long idx) {
+  return is_bf16 ? ld4(reinterpret_cast<const bf16*>(p) + idx)
+                 : ld4(reinterpret_cast<const float*>(p) + idx);
+}
+__device__ __forceinline__ void st4_any(void* p, int is_bf16, long long idx, float4 v) {
+  if (is_bf16) st4(reinterpret_cast<bf16*>(p) + idx, v);
+  else st4(reinterpret_cast<float*>(p) + idx, v);
+}
+__device__ __forceinline__ float ld1_any(const void* p, int is_bf16, long long idx) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p)[idx])
+                 : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st1_any(void* p, int is_bf16, long long idx, float v) {
+  if (is_bf16) reinterpret_cast<bf16*>(p)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+// out[m, :] = cat(h[m] (+ s*rh[m]), skip[m] (+ s*rs[m]))
+__global__ void __launch_bounds__(256)
+concat_inject_kernel(const void* h, int h_bf, int C1, const void* rh, int rh_bf, const void* skip,
+                     int skip_bf, int C2, const void* rs, int rs_bf, const float* cond_scale,
+                     int rows_per_sample, void* out, int out_bf, long long M) {
+  const int cv1 = C1 >> 2, cv = (C1 + C2) >> 2;
+  const long long total = M * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    long long m = i / cv;
+    int v = static_cast<int>(i - m * cv);
+    float s = cond_scale ? cond_scale[m / rows_per_sample] : 1.0f;
+    float4 a;
+    if (v < cv1) {
+      a = ld4_any(h, h_bf, m * C1 + v * 4);
+      if (rh) {
+        float4 r = ld4_any(rh, rh_bf, m * C1 + v * 4);
+        a.x += s * r.x; a.y += s * r.y; a.z += s * r.z; a.w += s * r.w;
+      }
+    } else {
+      int v2 = v - cv1;
+      a = ld4_any(skip, skip_bf, m * C2 + v2 * 4);
+      if (rs) {
+        float4 r = ld4_any(rs, rs_bf, m * C2 + v2 * 4);
+        a.x += s * r.x; a.y += s * r.y; a.z += s * r.z; a.w += s * r.w;
+      }
+    }
+    st4_any(out, out_bf, m * (C1 + C2) + v * 4, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const void* x, int x_bf, void* out, int out_bf, int n_img, int H, int W, int C) {
+  const int cv = C >> 2;
+  const long long total = static_cast<long long>(n_img) * (2 * H) * (2 * W) * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    int v = static_cast<int>(i % cv);
+    long long pix = i / cv;
+    int ox = static_cast<int>(pix % (2 * W));
+    int oy = static_cast<int>((pix / (2 * W)) % (2 * H));
+    long long n = pix / (4LL * W * H);
+    float4 a = ld4_any(x, x_bf, ((n * H + (oy >> 1)) * W + (ox >> 1)) * C + v * 4);
+    st4_any(out, out_bf, pix * C + v * 4, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+im2col3x3_s2_kernel(const void* x, int x_bf, void* out, int out_bf, int n_img, int H, int W, int C,
+                    int Ho, int Wo) {
+  const int cv = C >> 2;
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * 9 * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    int v = static_cast<int>(i % cv);
+    long long t = i / cv;
+    int tap = static_cast<int>(t % 9);
+    long long pix = t / 9;
+    int ox = static_cast<int>(pix % Wo);
+    int oy = static_cast<int>((pix / Wo) % Ho);
+    long long n = pix / (static_cast<long long>(Wo) * Ho);
+    int ky = tap / 3, kx = tap - ky * 3;
+    int y = oy * 2 + ky - 1, xx = ox * 2 + kx - 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < H && xx >= 0 && xx < W) a = ld4_any(x, x_bf, ((n * H + y) * W + xx) * C + v * 4);
+    st4_any(out, out_bf, (pix * 9 + tap) * C + v * 4, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast2d_kernel(const void* in, int in_bf, long long ld_in, void* out, int out_bf, long long ld_out,
+              long long rows, int cols) {
+  const int cv = cols >> 2;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    long long r = i / cv;
+    int v = static_cast<int>(i - r * cv);
+    st4_any(out, out_bf, r * ld_out + v * 4, ld4_any(in, in_bf, r * ld_in + v * 4));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+silu_kernel(const void* x, int x_bf, void* out, int out_bf, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+    st1_any(out, out_bf, i, silu_f(ld1_any(x, x_bf, i)));
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const void* a, int a_bf, const void* b, int b_bf, void* out, int out_bf, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+    st1_any(out, out_bf, i, ld1_any(a, a_bf, i) + ld1_any(b, b_bf, i));
+}
+
+// [cos | sin] of t * exp(-ln(10000) * k / half), fp32 like the reference (min_sdxl.py:205-224)
+__global__ void timestep_embedding_kernel(const float* t, int n, int dim, void* out, int out_bf) {
+  const int half = dim >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * half; i += gridDim.x * blockDim.x) {
+    int r = i / half, k = i - r * half;
+    float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+    float arg = t[r] * freq;
+    st1_any(out, out_bf, static_cast<long long>(r) * dim + k, cosf(arg));
+    st1_any(out, out_bf, static_cast<long long>(r) * dim + half + k, sinf(arg));
+  }
+}
+
+int grid_for(long long work_items) {
+  long long b = (work_items + 255) / 256;
+  long long cap = 8LL * sm_count();  // grid-stride: 8 resident CTAs of 256 threads per SM
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+}  // namespace iir
+
+using namespace iir;
+
+extern "C" int iir_concat_inject(const void* h, int h_dtype, int C1, const void* rh, int rh_dtype,
+                                 const void* skip, int skip_dtype, int C2, const void* rs,
+                                 int rs_dtype, const float* cond_scale, int rows_per_sample,
+                                 void* out, int out_dtype, int64_t M, void* stream) {
+  IIR_REQUIRE(h && out && C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && M > 0,
+              "iir_concat_inject: bad shape C1=%d C2=%d", C1, C2);
+  IIR_REQUIRE(C2 == 0 || skip, "iir_concat_inject: skip missing");
+  IIR_REQUIRE(!cond_scale || rows_per_sample > 0, "iir_concat_inject: rows_per_sample missing");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long work = M * ((C1 + C2) / 4);
+  concat_inject_kernel<<<grid_for(work), 256, 0, st>>>(
+      h, h_dtype == IIR_BF16, C1, rh, rh_dtype == IIR_BF16, skip, skip_dtype == IIR_BF16, C2, rs,
+      rs_dtype == IIR_BF16, cond_scale, rows_per_sample > 0 ? rows_per_sample : 1, out,
+      out_dtype == IIR_BF16, M);
+  count_launch();
+  return check_launch("iir_concat_inject");
+}
+
+extern "C" int iir_upsample2x(const void* x, int x_dtype, void* out, int out_dtype, int n_img, int H,
+                              int W, int C, void* stream) {
+  IIR_REQUIRE(x && out && n_img > 0 && H > 0 && W > 0 && C % 4 == 0, "iir_upsample2x: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long work = 4LL * n_img * H * W * (C / 4);
+  upsample2x_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_BF16, out,
+                                                    out_dtype == IIR_BF16, n_img, H, W, C);
+  count_launch();
+  return check_launch("iir_upsample2x");
+}
+
+extern "C" int iir_im2col3x3_s2(const void* x, int x_dtype, void* out, int out_dtype, int n_img,
+                                int H, int W, int C, void* stream) {
+  IIR_REQUIRE(x && out && n_img > 0 && H > 0 && W > 0 && C % 4 == 0, "iir_im2col3x3_s2: bad shape");
+  int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long work = 9LL * n_img * Ho * Wo * (C / 4);
+  im2col3x3_s2_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_BF16, out,
+                                                      out_dtype == IIR_BF16, n_img, H, W, C, Ho, Wo);
+  count_launch();
+  return check_launch("iir_im2col3x3_s2");
+}
+
+extern "C" int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
+                          int64_t ld_out, int64_t rows, int cols, void* stream) {
+  IIR_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0,
+              "iir_cast2d: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cast2d_kernel<<<grid_for(rows * (cols / 4)), 256, 0, st>>>(in, in_dtype == IIR_BF16, ld_in, out,
+                                                             out_dtype == IIR_BF16, ld_out, rows, cols);
+  count_launch();
+  return check_launch("iir_cast2d");
+}
+
+extern "C" int iir_silu(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, void* stream) {
+  IIR_REQUIRE(x && out && n > 0, "iir_silu: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  silu_kernel<<<grid_for(n), 256, 0, st>>>(x, x_dtype == IIR_BF16, out, out_dtype == IIR_BF16, n);
+  count_launch();
+  return check_launch("iir_silu");
+}
+
+extern "C" int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, void* out,
+                       int out_dtype, int64_t n, void* stream) {
+  IIR_REQUIRE(a && b && out && n > 0, "iir_add: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  add_kernel<<<grid_for(n), 256, 0, st>>>(a, a_dtype == IIR_BF16, b, b_dtype == IIR_BF16, out,
+                                          out_dtype == IIR_BF16, n);
+  count_launch();
+  return check_launch("iir_add");
+}
+
+extern "C" int iir_timestep_embedding(const float* t, int n, int dim, void* out, int out_dtype,
+                                      void* stream) {
+  IIR_REQUIRE(t && out && n > 0 && dim > 0 && dim % 2 == 0, "iir_timestep_embedding: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int work = n * dim / 2;
+  timestep_embedding_kernel<<<(work + 127) / 128, 128, 0, st>>>(t, n, dim, out, out_dtype == IIR_BF16);
+  count_launch();
+  return check_launch("iir_timestep_embedding");
+}

@@ -1,0 +1,448 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M, N] = epilogue( A[M, K] · W[N, K]ᵀ )      bf16 operands, fp32 accumulation in TMEM
+//
+// Design (B200-first):
+//   * persistent: one CTA per SM loops over 128 x BN output tiles (BN <= 256, runtime)
+//   * warp 0      : TMA producer — A and W tiles land in 128B-swizzled smem stages
+//   * warp 1      : single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators in TMEM,
+//                   two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1
+//   * warps 2..5  : epilogue — tcgen05.ld rows out of TMEM, fused bias / temb row-vector /
+//                   SiLU / GEGLU / SFT / residual add, bf16 or fp32 store
+//   * conv mode   : the A tile is a (Nt x Ht x Wt) pixel box of an NHWC tensor fetched with a 4-D
+//                   TMA map at the tap offset (kx-1, ky-1); out-of-bounds box elements are
+//                   zero-filled by TMA, which *is* the conv's zero padding. No im2col buffer.
+//
+// Replaces: nn.Linear / nn.Conv2d + following elementwise ops of the reference
+// (module/min_sdxl.py:246-283,301-307,502-523,569-573; module/aggregator.py:63-90).
+#include "common.cuh"
+
+namespace iir {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
+
+struct alignas(64) GemmTcParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int M, N, K, num_kb;
+  int conv, n_img, H, W, Cin;
+  int Wt, Ht, Nt, tiles_x, tiles_y, tiles_img;
+  int tiles_m, tiles_n, BN, stages;
+  const float* bias;
+  const float* rowvec;
+  int rows_per_sample;
+  const void* residual;
+  int res_bf16;
+  long long ld_res;
+  const void* aux;
+  int aux_bf16;
+  long long ld_aux;
+  void* out;
+  int out_bf16;
+  long long ld_out;
+  int act;
+};
+
+struct TileCoord {
+  int m0;          // linear: first row
+  int n_img0, y0, x0;  // conv: first image / row / column of the pixel box
+  int n0;          // first weight row (column of the packed output)
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int tile) {
+  TileCoord c;
+  int tn = tile / p.tiles_m;
+  int tm = tile - tn * p.tiles_m;
+  c.n0 = tn * p.BN;
+  c.m0 = tm * BM;
+  c.n_img0 = c.y0 = c.x0 = 0;
+  if (p.conv) {
+    int tx = tm % p.tiles_x;
+    int t2 = tm / p.tiles_x;
+    int ty = t2 % p.tiles_y;
+    int ti = t2 / p.tiles_y;
+    c.x0 = tx * p.Wt;
+    c.y0 = ty * p.Ht;
+    c.n_img0 = ti * p.Nt;
+  }
+  return c;
+}
+
+template <int PAIR>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cpb = p.conv ? p.Cin / BK : 1;  // 64-channel blocks per filter tap
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        TileCoord c = tile_coord(p, tile);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          if (p.conv) {
+            int tap = kb / cpb;
+            int cb = kb - tap * cpb;
+            int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * BK, c.x0 + kx - 1, c.y0 + ky - 1,
+                        c.n_img0);
+          } else {
+            tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BK, c.m0);
+          }
+          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, p.BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_i = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_i) {
+        const uint32_t buf = acc_i & 1;
+        const uint32_t acc_phase = (acc_i >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * ACC_STRIDE;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t adesc = umma_desc_sw128(sa + k * 32, 16, 1024);
+            uint64_t bdesc = umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int lane_base = (warp & 3) * 32;  // TMEM lane quarter this warp may access
+    const int row = lane_base + lane;
+    const int half = p.BN >> 1;
+    const int n_out_total = PAIR ? (p.N >> 1) : p.N;
+    uint32_t acc_i = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_i) {
+      const uint32_t buf = acc_i & 1;
+      const uint32_t acc_phase = (acc_i >> 1) & 1;
+      TileCoord c = tile_coord(p, tile);
+      long long m_out;
+      bool valid;
+      if (p.conv) {
+        int xi = row % p.Wt;
+        int t2 = row / p.Wt;
+        int yi = t2 % p.Ht;
+        int ni = t2 / p.Ht;
+        int x = c.x0 + xi, y = c.y0 + yi, n = c.n_img0 + ni;
+        valid = (x < p.W) && (y < p.H) && (n < p.n_img);
+        m_out = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      } else {
+        m_out = c.m0 + row;
+        valid = m_out < p.M;
+      }
+      const int sample = valid ? static_cast<int>(m_out / p.rows_per_sample) : 0;
+
+      mbar_wait(&tfull_bar[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
+      const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
+      const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
+      for (int cc = 0; cc < ncols; cc += 32) {
+        uint32_t r[32];
+        uint32_t r2[32];
+        tmem_ld32(taddr + cc, r);
+        if (PAIR) tmem_ld32(taddr + half + cc, r2);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+          const int pn = c.n0 + cc;  // packed column of r[0]
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (pn + j < p.N) {
+                float4 b = ld4(p.bias + pn + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.rowvec) {
+            const float* rv = p.rowvec + static_cast<long long>(sample) * p.N + pn;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (pn + j < p.N) {
+                float4 b = ld4(rv + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.act == IIR_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          } else if (p.act == IIR_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          }
+          const int on = nout0 + cc;  // output column of v[0]
+          if (PAIR) {
+            float g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r2[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (pn + half + j < p.N) {
+                  float4 b = ld4(p.bias + pn + half + j);
+                  g[j] += b.x; g[j + 1] += b.y; g[j + 2] += b.z; g[j + 3] += b.w;
+                }
+              }
+            }
+            if (PAIR == IIR_PAIR_GEGLU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
+            } else {  // SFT: h * (gamma + 1) + beta
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (on + j < n_out_total) {
+                  float4 h = p.aux_bf16
+                      ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.aux) + m_out * p.ld_aux + on + j)
+                      : ld4(reinterpret_cast<const float*>(p.aux) + m_out * p.ld_aux + on + j);
+                  v[j] = h.x * (v[j] + 1.0f) + g[j];
+                  v[j + 1] = h.y * (v[j + 1] + 1.0f) + g[j + 1];
+                  v[j + 2] = h.z * (v[j + 2] + 1.0f) + g[j + 2];
+                  v[j + 3] = h.w * (v[j + 3] + 1.0f) + g[j + 3];
+                }
+              }
+            }
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (on + j < n_out_total) {
+                float4 q = p.res_bf16
+                    ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.residual) + m_out * p.ld_res + on + j)
+                    : ld4(reinterpret_cast<const float*>(p.residual) + m_out * p.ld_res + on + j);
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              }
+            }
+          }
+          if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_out * p.ld_out + on;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (on + j < n_out_total) {
+                uint4 u;
+                u.x = pack_bf16(v[j], v[j + 1]);
+                u.y = pack_bf16(v[j + 2], v[j + 3]);
+                u.z = pack_bf16(v[j + 4], v[j + 5]);
+                u.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + m_out * p.ld_out + on;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (on + j < n_out_total)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int pow2_floor(int v) {
+  int r = 1;
+  while (r * 2 <= v) r *= 2;
+  return r;
+}
+int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r *= 2;
+  return r;
+}
+
+}  // namespace
+
+}  // namespace iir
+
+extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
+  using namespace iir;
+  IIR_REQUIRE(a != nullptr, "iir_gemm_tc: null args");
+  IIR_REQUIRE(a->a_dtype == IIR_BF16 && a->w_dtype == IIR_BF16,
+              "iir_gemm_tc: operands must be bf16 (use iir_gemm_simt for the fp32 check mode)");
+  IIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "iir_gemm_tc: empty problem M=%d N=%d K=%d", a->M,
+              a->N, a->K);
+  IIR_REQUIRE(a->K % 8 == 0, "iir_gemm_tc: K=%d must be a multiple of 8", a->K);
+  IIR_REQUIRE(a->bn >= 32 && a->bn <= 256 && a->bn % 32 == 0, "iir_gemm_tc: bad bn=%d", a->bn);
+  IIR_REQUIRE(a->pair == IIR_PAIR_NONE || (a->bn % 64 == 0 && a->N % a->bn == 0),
+              "iir_gemm_tc: paired epilogue needs bn%%64==0 and N%%bn==0 (N=%d bn=%d)", a->N, a->bn);
+  IIR_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+              "iir_gemm_tc: pointers must be 16-byte aligned");
+  const int n_out = a->pair ? a->N / 2 : a->N;
+  IIR_REQUIRE(n_out % 8 == 0 && a->ld_out % 8 == 0, "iir_gemm_tc: N_out=%d / ld_out must be multiples of 8", n_out);
+  IIR_REQUIRE(!a->residual || a->ld_res % 4 == 0, "iir_gemm_tc: ld_res must be a multiple of 4");
+  IIR_REQUIRE(a->pair != IIR_PAIR_SFT || a->aux, "iir_gemm_tc: SFT epilogue needs aux (h)");
+  IIR_REQUIRE(a->rows_per_sample > 0 || !a->rowvec, "iir_gemm_tc: rowvec needs rows_per_sample");
+
+  GemmTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_kb = (a->K + BK - 1) / BK;
+  p.BN = a->bn;
+  p.tiles_n = (a->N + a->bn - 1) / a->bn;
+  p.conv = a->conv ? 1 : 0;
+  CUresult cr;
+  if (a->conv) {
+    IIR_REQUIRE(a->conv == 3 && a->stride == 1 && a->up2 == 0,
+                "iir_gemm_tc: conv mode supports 3x3 stride 1 only");
+    IIR_REQUIRE(a->Cin % BK == 0 && a->K == 9 * a->Cin, "iir_gemm_tc: conv needs Cin%%64==0, K==9*Cin");
+    IIR_REQUIRE(a->M == a->n_img * a->H * a->W, "iir_gemm_tc: conv M mismatch");
+    p.n_img = a->n_img; p.H = a->H; p.W = a->W; p.Cin = a->Cin;
+    int Wt = 0;
+    for (int cand = 128; cand >= 8; cand >>= 1)
+      if (a->W % cand == 0) { Wt = cand; break; }
+    if (Wt == 0) Wt = pow2_ceil(a->W) > 128 ? 128 : pow2_ceil(a->W);
+    int Ht = 128 / Wt;
+    if (Ht > pow2_ceil(a->H)) Ht = pow2_ceil(a->H);
+    int Nt = 128 / (Wt * Ht);
+    p.Wt = Wt; p.Ht = Ht; p.Nt = Nt;
+    p.tiles_x = (a->W + Wt - 1) / Wt;
+    p.tiles_y = (a->H + Ht - 1) / Ht;
+    p.tiles_img = (a->n_img + Nt - 1) / Nt;
+    p.tiles_m = p.tiles_x * p.tiles_y * p.tiles_img;
+    uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+    uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->W * a->Cin * 2,
+                           (uint64_t)a->H * a->W * a->Cin * 2};
+    uint32_t box[4] = {BK, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
+    cr = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->a, dims, strides, box,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    IIR_REQUIRE(a->lda % 8 == 0 && a->lda >= a->K, "iir_gemm_tc: lda=%lld invalid", (long long)a->lda);
+    p.tiles_m = (a->M + BM - 1) / BM;
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    cr = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, dims, strides, box,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (cr != CUDA_SUCCESS) {
+    set_error("iir_gemm_tc: cuTensorMapEncodeTiled(A) failed (%d)", (int)cr);
+    return IIR_ERR_CUDA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->K * 2};
+    uint32_t box[2] = {BK, (uint32_t)a->bn};
+    cr = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w, dims, strides, box,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+    if (cr != CUDA_SUCCESS) {
+      set_error("iir_gemm_tc: cuTensorMapEncodeTiled(W) failed (%d)", (int)cr);
+      return IIR_ERR_CUDA;
+    }
+  }
+  p.bias = a->bias;
+  p.rowvec = a->rowvec;
+  p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
+  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_BF16; p.ld_res = a->ld_res;
+  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_BF16; p.ld_aux = a->ld_aux;
+  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_BF16; p.ld_out = a->ld_out;
+  p.act = a->act;
+
+  const int stage_bytes = A_STAGE_BYTES + a->bn * BK * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  int grid = sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+
+  cudaError_t e;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define LAUNCH(PAIRV)                                                                              \
+  e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           (int)smem);                                                             \
+  if (e == cudaSuccess) gemm_tc_kernel<PAIRV><<<grid, GEMM_THREADS, smem, st>>>(p);
+  if (a->pair == IIR_PAIR_NONE) { LAUNCH(0) }
+  else if (a->pair == IIR_PAIR_GEGLU) { LAUNCH(1) }
+  else if (a->pair == IIR_PAIR_SFT) { LAUNCH(2) }
+  else { set_error("iir_gemm_tc: bad pair=%d", a->pair); return IIR_ERR_INVALID; }
+#undef LAUNCH
+  if (e != cudaSuccess) {
+    set_error("iir_gemm_tc: %s", cudaGetErrorString(e));
+    return IIR_ERR_CUDA;
+  }
+  count_launch();
+  return check_launch("iir_gemm_tc");
+}

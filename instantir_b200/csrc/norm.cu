@@ -1,0 +1,260 @@
+// GroupNorm(+SiLU) and LayerNorm(+adaLN) over NHWC / token-major activations.
+// HBM-bound: every element is read twice (stats, apply) and written once; reads are coalesced
+// float4 / 8-byte bf16x4 vectors, partial sums are reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace iir {
+namespace {
+
+constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_THREADS = 256;
+
+// ---- stage 1: per (image, row-chunk) partial sum / sum of squares for every group ------------
+// grid (chunks, n_img); thread t: vector lane tv = t%64 walks channel vectors, row lane tr = t/64.
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, int HW, int C, int groups,
+                int rows_per_chunk) {
+  extern __shared__ float sm[];  // [4][C] sums, [4][C] squares
+  float* s_sum = sm;
+  float* s_sq = sm + 4 * C;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int tv = threadIdx.x & 63, tr = threadIdx.x >> 6;
+  const int cv = C >> 2;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  const T* base = x + static_cast<long long>(img) * HW * C;
+  for (int v = tv; v < cv; v += 64) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int r = r0 + tr; r < r1; r += 4) {
+      float4 a = ld4(base + static_cast<long long>(r) * C + v * 4);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x += a.x * a.x; q.y += a.y * a.y; q.z += a.z * a.z; q.w += a.w * a.w;
+    }
+    float* ps = s_sum + tr * C + v * 4;
+    float* pq = s_sq + tr * C + v * 4;
+    ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
+    pq[0] = q.x; pq[1] = q.y; pq[2] = q.z; pq[3] = q.w;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (int tr2 = 0; tr2 < 4; ++tr2)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        s += s_sum[tr2 * C + c];
+        q += s_sq[tr2 * C + c];
+      }
+    float* o = partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + chunk) * groups + g) * 2;
+    o[0] = static_cast<float>(s);
+    o[1] = static_cast<float>(q);
+  }
+}
+
+// ---- stage 2: normalise, affine, optional SiLU ---------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ partials,
+                TO* __restrict__ out, int HW, int C, int groups, int nchunks, float eps, int silu,
+                int rows_per_block) {
+  extern __shared__ float sm[];  // [C] scale, [C] shift
+  float* s_scale = sm;
+  float* s_shift = sm + C;
+  __shared__ float s_mean[64], s_rstd[64];
+  const int img = blockIdx.y;
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const float* pp = partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + ch) * groups + g) * 2;
+      s += pp[0];
+      q += pp[1];
+    }
+    double n = static_cast<double>(HW) * cpg;
+    double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    int g = c / cpg;
+    float sc = s_rstd[g] * (gamma ? gamma[c] : 1.0f);
+    s_scale[c] = sc;
+    s_shift[c] = (beta ? beta[c] : 0.0f) - s_mean[g] * sc;
+  }
+  __syncthreads();
+  const int cv = C >> 2;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const long long total = static_cast<long long>(r1 - r0) * cv;
+  const TI* xb = x + (static_cast<long long>(img) * HW + r0) * C;
+  TO* ob = out + (static_cast<long long>(img) * HW + r0) * C;
+  for (long long i = threadIdx.x; i < total; i += GN_THREADS) {
+    int v = static_cast<int>(i % cv);
+    float4 a = ld4(xb + i * 4);
+    const float* sc = s_scale + v * 4;
+    const float* sh = s_shift + v * 4;
+    a.x = a.x * sc[0] + sh[0];
+    a.y = a.y * sc[1] + sh[1];
+    a.z = a.z * sc[2] + sh[2];
+    a.w = a.w * sc[3] + sh[3];
+    if (silu) { a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w); }
+    st4(ob + i * 4, a);
+  }
+}
+
+// ---- LayerNorm: one warp per row, row cached in registers ----------------------------------
+constexpr int LN_MAX_V = 16;  // float4 per lane -> C <= 2048
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ mod, int rows_per_sample,
+                 TO* __restrict__ out, int rows, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + warp;
+  if (row >= rows) return;
+  const int cv = C >> 2;
+  const TI* xr = x + row * C;
+  float4 v[LN_MAX_V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      v[j] = ld4(xr + i * 4);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+  const float rstd = rsqrtf(q / C + eps);
+  const float* shift = nullptr;
+  const float* scale = nullptr;
+  if (mod) {
+    const float* m = mod + (row / rows_per_sample) * 2LL * C;
+    shift = m;       // emb.chunk(2): shift first, then scale (attention_processor.py:24)
+    scale = m + C;
+  }
+  TO* orow = out + row * C;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      float4 a = v[j];
+      a.x = (a.x - mean) * rstd; a.y = (a.y - mean) * rstd;
+      a.z = (a.z - mean) * rstd; a.w = (a.w - mean) * rstd;
+      if (gamma) {
+        float4 g = ld4(gamma + i * 4);
+        a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
+      }
+      if (beta) {
+        float4 b = ld4(beta + i * 4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (mod) {
+        float4 sc = ld4(scale + i * 4), sh = ld4(shift + i * 4);
+        a.x = a.x * (1.f + sc.x) + sh.x; a.y = a.y * (1.f + sc.y) + sh.y;
+        a.z = a.z * (1.f + sc.z) + sh.z; a.w = a.w * (1.f + sc.w) + sh.w;
+      }
+      st4(orow + i * 4, a);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace iir
+
+using namespace iir;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int64_t iir_groupnorm_scratch_floats(int n_img, int groups) {
+  return static_cast<int64_t>(n_img) * GN_MAX_CHUNKS * groups * 2;
+}
+
+extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta,
+                             void* out, int out_dtype, int n_img, int HW, int C, int groups,
+                             float eps, int silu, float* partials, void* stream) {
+  IIR_REQUIRE(x && out && partials, "iir_groupnorm: null pointer");
+  IIR_REQUIRE(n_img > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64 && C % groups == 0 &&
+                  C % 4 == 0,
+              "iir_groupnorm: bad shape n=%d HW=%d C=%d G=%d", n_img, HW, C, groups);
+  IIR_REQUIRE(8 * C * sizeof(float) <= 200 * 1024, "iir_groupnorm: C=%d too large", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // enough chunks to fill the machine, at most GN_MAX_CHUNKS, at least 16 rows each
+  int want = (2 * sm_count() + n_img - 1) / n_img;
+  int nchunks = want < 1 ? 1 : (want > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : want);
+  int rpc = (HW + nchunks - 1) / nchunks;
+  if (rpc < 16) rpc = 16;
+  nchunks = (HW + rpc - 1) / rpc;
+  size_t smem1 = 8 * (size_t)C * sizeof(float);
+  dim3 g1(nchunks, n_img);
+  cudaError_t e = cudaSuccess;
+  if (x_dtype == IIR_F32) {
+    if (smem1 > 48 * 1024)
+      e = cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    gn_stats_kernel<float><<<g1, GN_THREADS, smem1, st>>>(reinterpret_cast<const float*>(x), partials, HW, C, groups, rpc);
+  } else {
+    if (smem1 > 48 * 1024)
+      e = cudaFuncSetAttribute(gn_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    gn_stats_kernel<bf16><<<g1, GN_THREADS, smem1, st>>>(reinterpret_cast<const bf16*>(x), partials, HW, C, groups, rpc);
+  }
+  if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
+  count_launch();
+  int rc = check_launch("iir_groupnorm(stats)");
+  if (rc) return rc;
+  // apply: blocks of >= 8 rows, ~4 waves
+  int blocks_per_img = (4 * sm_count() + n_img - 1) / n_img;
+  int rpb = (HW + blocks_per_img - 1) / blocks_per_img;
+  if (rpb < 8) rpb = 8;
+  blocks_per_img = (HW + rpb - 1) / rpb;
+  dim3 g2(blocks_per_img, n_img);
+  size_t smem2 = 2 * (size_t)C * sizeof(float);
+#define GO(TI, TO)                                                                                 \
+  gn_apply_kernel<TI, TO><<<g2, GN_THREADS, smem2, st>>>(                                          \
+      reinterpret_cast<const TI*>(x), gamma, beta, partials, reinterpret_cast<TO*>(out), HW, C,    \
+      groups, nchunks, eps, silu, rpb)
+  if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
+  else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
+  else if (x_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else GO(bf16, bf16);
+#undef GO
+  count_launch();
+  return check_launch("iir_groupnorm(apply)");
+}
+
+extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta,
+                             const float* mod, int rows_per_sample, void* out, int out_dtype,
+                             int rows, int C, float eps, void* stream) {
+  IIR_REQUIRE(x && out && rows > 0 && C > 0 && C % 4 == 0 && C <= LN_MAX_V * 128,
+              "iir_layernorm: bad shape rows=%d C=%d (C%%4==0, C<=%d)", rows, C, LN_MAX_V * 128);
+  IIR_REQUIRE(!mod || rows_per_sample > 0, "iir_layernorm: mod needs rows_per_sample");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = (rows + 7) / 8;
+#define GO(TI, TO)                                                                              \
+  layernorm_kernel<TI, TO><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, \
+                                                   mod, rows_per_sample,                        \
+                                                   reinterpret_cast<TO*>(out), rows, C, eps)
+  if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
+  else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
+  else if (x_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else GO(bf16, bf16);
+#undef GO
+  count_launch();
+  return check_launch("iir_layernorm");
+}

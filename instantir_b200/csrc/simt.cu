@@ -1,0 +1,388 @@
+// fp32 SIMT kernels: the north star's "fp32 check mode" (<=1e-4 vs the oracle) and the on-GPU
+// cross-check of the tcgen05 kernels, plus the tiny-channel direct convolution (conv_in/conv_out)
+// and the small-M linear used by the time-embedding / adaLN projections.
+#include "common.cuh"
+
+namespace iir {
+namespace {
+
+// ------------------------------------------------------------------------------ SIMT GEMM
+struct GemmSimtParams {
+  const void* a;
+  const void* w;
+  int M, N, K;
+  long long lda;
+  int conv, n_img, H, W, Cin, stride, up2, Ho, Wo;
+  const float* bias;
+  const float* rowvec;
+  int rows_per_sample;
+  const void* residual; int res_bf16; long long ld_res;
+  const void* aux; int aux_bf16; long long ld_aux;
+  void* out; int out_bf16; long long ld_out;
+  int act, bn;
+};
+
+template <typename TA>
+__device__ __forceinline__ float load_a(const GemmSimtParams& p, int m, int k) {
+  const TA* A = reinterpret_cast<const TA*>(p.a);
+  if (!p.conv) return ld_f(A + static_cast<long long>(m) * p.lda + k);
+  int tap = k / p.Cin;
+  int c = k - tap * p.Cin;
+  int ky = tap / 3, kx = tap - ky * 3;
+  int hw = p.Ho * p.Wo;
+  int n = m / hw;
+  int r = m - n * hw;
+  int oy = r / p.Wo, ox = r - oy * p.Wo;
+  int y = oy * p.stride + ky - 1, x = ox * p.stride + kx - 1;
+  if (y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.0f;
+  int sh = p.H, sw = p.W;
+  if (p.up2) { y >>= 1; x >>= 1; sh >>= 1; sw >>= 1; }
+  return ld_f(A + ((static_cast<long long>(n) * sh + y) * sw + x) * p.Cin + c);
+}
+
+constexpr int ST = 64;   // tile edge
+constexpr int SK = 16;   // k step
+
+template <typename TA, typename TW, int PAIR>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) {
+  __shared__ float As[SK][ST + 1];
+  __shared__ float Ws[SK][ST + 1];
+  __shared__ float Ws2[PAIR ? SK : 1][ST + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * ST;
+  const int o0 = blockIdx.x * ST;  // first OUTPUT column of the tile
+  const int n_out = PAIR ? p.N / 2 : p.N;
+  const int half = p.bn / 2;
+  const TW* Wp = reinterpret_cast<const TW*>(p.w);
+  float acc[4][4] = {};
+  float acc2[4][4] = {};
+  for (int k0 = 0; k0 < p.K; k0 += SK) {
+    for (int i = threadIdx.x; i < ST * SK; i += 256) {
+      int r = i / SK, kk = i - r * SK;
+      int m = m0 + r, k = k0 + kk;
+      As[kk][r] = (m < p.M && k < p.K) ? load_a<TA>(p, m, k) : 0.0f;
+      int on = o0 + r;
+      float w1 = 0.f, w2 = 0.f;
+      if (on < n_out && k < p.K) {
+        if (PAIR) {
+          int t = on / half, rr = on - t * half;
+          long long pn = static_cast<long long>(t) * p.bn + rr;
+          w1 = ld_f(Wp + pn * p.K + k);
+          w2 = ld_f(Wp + (pn + half) * p.K + k);
+        } else {
+          w1 = ld_f(Wp + static_cast<long long>(on) * p.K + k);
+        }
+      }
+      Ws[kk][r] = w1;
+      if (PAIR) Ws2[kk][r] = w2;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SK; ++kk) {
+      float av[4], wv[4], wv2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = As[kk][ty * 4 + i];
+        wv[i] = Ws[kk][tx * 4 + i];
+        if (PAIR) wv2[i] = Ws2[kk][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+          if (PAIR) acc2[i][j] = fmaf(av[i], wv2[j], acc2[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    int sample = m / p.rows_per_sample;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int on = o0 + tx * 4 + j;
+      if (on >= n_out) continue;
+      long long pn = on, pn2 = 0;
+      if (PAIR) {
+        int t = on / half, rr = on - t * half;
+        pn = static_cast<long long>(t) * p.bn + rr;
+        pn2 = pn + half;
+      }
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[pn];
+      if (p.rowvec) v += p.rowvec[static_cast<long long>(sample) * p.N + pn];
+      if (p.act == IIR_ACT_SILU) v = silu_f(v);
+      else if (p.act == IIR_ACT_GELU) v = gelu_erf_f(v);
+      if (PAIR) {
+        float g = acc2[i][j];
+        if (p.bias) g += p.bias[pn2];
+        if (PAIR == IIR_PAIR_GEGLU) {
+          v = v * gelu_erf_f(g);
+        } else {
+          float h = p.aux_bf16
+              ? ld_f(reinterpret_cast<const __nv_bfloat16*>(p.aux) + m * p.ld_aux + on)
+              : ld_f(reinterpret_cast<const float*>(p.aux) + m * p.ld_aux + on);
+          v = h * (v + 1.0f) + g;
+        }
+      }
+      if (p.residual) {
+        v += p.res_bf16
+            ? ld_f(reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ld_res + on)
+            : ld_f(reinterpret_cast<const float*>(p.residual) + m * p.ld_res + on);
+      }
+      if (p.out_bf16) st_f(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ld_out + on, v);
+      else st_f(reinterpret_cast<float*>(p.out) + m * p.ld_out + on, v);
+    }
+  }
+}
+
+template <typename TA, typename TW>
+void launch_gemm_simt(const GemmSimtParams& p, int pair, cudaStream_t st) {
+  int n_out = pair ? p.N / 2 : p.N;
+  dim3 grid((n_out + ST - 1) / ST, (p.M + ST - 1) / ST);
+  if (pair == IIR_PAIR_NONE) gemm_simt_kernel<TA, TW, 0><<<grid, 256, 0, st>>>(p);
+  else if (pair == IIR_PAIR_GEGLU) gemm_simt_kernel<TA, TW, 1><<<grid, 256, 0, st>>>(p);
+  else gemm_simt_kernel<TA, TW, 2><<<grid, 256, 0, st>>>(p);
+}
+
+// ------------------------------------------------------------------- direct 3x3 conv (tiny C)
+// one thread per (pixel, cout); weights [Cout,3,3,Cin] fp32.
+template <typename TI, typename TO>
+__global__ void conv3x3_direct_kernel(const TI* __restrict__ in, int in_nchw,
+                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                      TO* __restrict__ out, int out_nchw, int n_img, int H, int W,
+                                      int Cin, int Cout, int out_H, int out_row_off) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(n_img) * H * W * Cout;
+  if (idx >= total) return;
+  int co = static_cast<int>(idx % Cout);
+  long long pix = idx / Cout;
+  int x = static_cast<int>(pix % W);
+  int y = static_cast<int>((pix / W) % H);
+  int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float acc = bias ? bias[co] : 0.0f;
+  for (int ky = 0; ky < 3; ++ky) {
+    int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      int xx = x + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float* wp = w + ((co * 3 + ky) * 3 + kx) * Cin;
+      if (in_nchw) {
+        for (int c = 0; c < Cin; ++c)
+          acc = fmaf(ld_f(in + ((static_cast<long long>(n) * Cin + c) * H + yy) * W + xx), wp[c], acc);
+      } else {
+        const TI* ip = in + ((static_cast<long long>(n) * H + yy) * W + xx) * Cin;
+        for (int c = 0; c < Cin; ++c) acc = fmaf(ld_f(ip + c), wp[c], acc);
+      }
+    }
+  }
+  if (out_nchw) {
+    st_f(out + ((static_cast<long long>(n) * Cout + co) * H + y) * W + x, acc);
+  } else {
+    st_f(out + ((static_cast<long long>(n) * out_H + out_row_off + y) * W + x) * Cout + co, acc);
+  }
+}
+
+// ------------------------------------------------------------------------- SIMT attention
+// One warp per query row, head_dim 64 (two dims per lane). Online softmax per key segment.
+struct AttnSimtParams {
+  const void* q; long long ldq; int q_off;
+  int n_seg;
+  const void* k[2]; long long ldk[2]; int k_off[2];
+  const void* v[2]; long long ldv[2]; int v_off[2];
+  int kv_len[2];
+  float seg_scale[2];
+  void* out; long long ldo; int out_off;
+  int B, heads, n_q;
+  float scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_simt_kernel(const AttnSimtParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + warp;  // flattened (b, h, i)
+  const long long total = static_cast<long long>(p.B) * p.heads * p.n_q;
+  if (row >= total) return;
+  const int i = static_cast<int>(row % p.n_q);
+  const int h = static_cast<int>((row / p.n_q) % p.heads);
+  const int b = static_cast<int>(row / (static_cast<long long>(p.n_q) * p.heads));
+  const T* Q = reinterpret_cast<const T*>(p.q) + (static_cast<long long>(b) * p.n_q + i) * p.ldq +
+               p.q_off + h * 64;
+  const float q0 = ld_f(Q + lane * 2) * p.scale, q1 = ld_f(Q + lane * 2 + 1) * p.scale;
+  float o0 = 0.f, o1 = 0.f;
+  for (int s = 0; s < p.n_seg; ++s) {
+    const T* K = reinterpret_cast<const T*>(p.k[s]) +
+                 static_cast<long long>(b) * p.kv_len[s] * p.ldk[s] + p.k_off[s] + h * 64;
+    const T* V = reinterpret_cast<const T*>(p.v[s]) +
+                 static_cast<long long>(b) * p.kv_len[s] * p.ldv[s] + p.v_off[s] + h * 64;
+    float mx = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < p.kv_len[s]; ++j) {
+      const T* kr = K + static_cast<long long>(j) * p.ldk[s];
+      float d = q0 * ld_f(kr + lane * 2) + q1 * ld_f(kr + lane * 2 + 1);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      float mn = fmaxf(mx, d);
+      float corr = __expf(mx - mn);
+      float pj = __expf(d - mn);
+      const T* vr = V + static_cast<long long>(j) * p.ldv[s];
+      l = l * corr + pj;
+      a0 = a0 * corr + pj * ld_f(vr + lane * 2);
+      a1 = a1 * corr + pj * ld_f(vr + lane * 2 + 1);
+      mx = mn;
+    }
+    float inv = p.seg_scale[s] / l;
+    o0 += a0 * inv;
+    o1 += a1 * inv;
+  }
+  T* O = reinterpret_cast<T*>(p.out) + (static_cast<long long>(b) * p.n_q + i) * p.ldo + p.out_off +
+         h * 64;
+  st_f(O + lane * 2, o0);
+  st_f(O + lane * 2 + 1, o1);
+}
+
+// --------------------------------------------------------------------------- small-M linear
+// out[m, n] = act(sum_k x[m,k] w[n,k] + bias[n]); one warp per output column n, M <= 16.
+template <typename TX, typename TW, typename TO>
+__global__ void __launch_bounds__(256) linear_small_kernel(const TX* __restrict__ x,
+                                                           const TW* __restrict__ w,
+                                                           const float* __restrict__ bias,
+                                                           TO* __restrict__ out, int M, int N, int K,
+                                                           int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+  const TW* wr = w + static_cast<long long>(n) * K;
+  for (int k = lane; k < K; k += 32) {
+    float wv = ld_f(wr + k);
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+      if (m < M) acc[m] = fmaf(ld_f(x + static_cast<long long>(m) * K + k), wv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    if (m < M) {
+      float v = acc[m];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) {
+        if (bias) v += bias[n];
+        if (act == IIR_ACT_SILU) v = silu_f(v);
+        else if (act == IIR_ACT_GELU) v = gelu_erf_f(v);
+        st_f(out + static_cast<long long>(m) * N + n, v);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace iir
+
+using namespace iir;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
+  IIR_REQUIRE(a != nullptr, "iir_gemm_simt: null args");
+  IIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "iir_gemm_simt: empty problem");
+  IIR_REQUIRE(a->pair == IIR_PAIR_NONE || (a->bn > 0 && a->bn % 2 == 0 && a->N % a->bn == 0),
+              "iir_gemm_simt: paired epilogue needs N%%bn==0");
+  GemmSimtParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = a->a; p.w = a->w; p.M = a->M; p.N = a->N; p.K = a->K; p.lda = a->lda;
+  p.conv = a->conv;
+  if (a->conv) {
+    IIR_REQUIRE(a->conv == 3 && (a->stride == 1 || a->stride == 2), "iir_gemm_simt: 3x3 s1/s2 only");
+    IIR_REQUIRE(a->K == 9 * a->Cin, "iir_gemm_simt: K must be 9*Cin");
+    p.n_img = a->n_img; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.stride = a->stride; p.up2 = a->up2;
+    p.Ho = (a->H + 2 - 3) / a->stride + 1;
+    p.Wo = (a->W + 2 - 3) / a->stride + 1;
+    IIR_REQUIRE(a->M == a->n_img * p.Ho * p.Wo, "iir_gemm_simt: conv M mismatch (M=%d, expect %d)",
+                a->M, a->n_img * p.Ho * p.Wo);
+  }
+  p.bias = a->bias; p.rowvec = a->rowvec;
+  p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
+  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_BF16; p.ld_res = a->ld_res;
+  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_BF16; p.ld_aux = a->ld_aux;
+  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_BF16; p.ld_out = a->ld_out;
+  p.act = a->act; p.bn = a->bn > 0 ? a->bn : 2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->a_dtype == IIR_F32 && a->w_dtype == IIR_F32) launch_gemm_simt<float, float>(p, a->pair, st);
+  else if (a->a_dtype == IIR_BF16 && a->w_dtype == IIR_BF16) launch_gemm_simt<bf16, bf16>(p, a->pair, st);
+  else if (a->a_dtype == IIR_F32 && a->w_dtype == IIR_BF16) launch_gemm_simt<float, bf16>(p, a->pair, st);
+  else launch_gemm_simt<bf16, float>(p, a->pair, st);
+  count_launch();
+  return check_launch("iir_gemm_simt");
+}
+
+extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, const float* w,
+                                  const float* bias, void* out, int out_dtype, int out_nchw,
+                                  int n_img, int H, int W, int Cin, int Cout, int out_H,
+                                  int out_row_off, void* stream) {
+  IIR_REQUIRE(in && w && out && n_img > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0,
+              "iir_conv3x3_direct: bad args");
+  IIR_REQUIRE(out_nchw || (out_H >= H + out_row_off && out_row_off >= 0),
+              "iir_conv3x3_direct: output window out of range");
+  long long total = static_cast<long long>(n_img) * H * W * Cout;
+  int blocks = static_cast<int>((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define GO(TI, TO)                                                                               \
+  conv3x3_direct_kernel<TI, TO><<<blocks, 256, 0, st>>>(                                         \
+      reinterpret_cast<const TI*>(in), in_nchw, w, bias, reinterpret_cast<TO*>(out), out_nchw,   \
+      n_img, H, W, Cin, Cout, out_H, out_row_off)
+  if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
+  else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
+  else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else GO(bf16, bf16);
+#undef GO
+  count_launch();
+  return check_launch("iir_conv3x3_direct");
+}
+
+extern "C" int iir_attn_simt(const iir_attn_args* a, void* stream) {
+  IIR_REQUIRE(a != nullptr && a->n_seg >= 1 && a->n_seg <= 2, "iir_attn_simt: bad args");
+  AttnSimtParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = a->q; p.ldq = a->ldq; p.q_off = a->q_off; p.n_seg = a->n_seg;
+  for (int s = 0; s < a->n_seg; ++s) {
+    IIR_REQUIRE(a->kv_len[s] > 0, "iir_attn_simt: empty key segment %d", s);
+    p.k[s] = a->k[s]; p.ldk[s] = a->ldk[s]; p.k_off[s] = a->k_off[s];
+    p.v[s] = a->v[s]; p.ldv[s] = a->ldv[s]; p.v_off[s] = a->v_off[s];
+    p.kv_len[s] = a->kv_len[s]; p.seg_scale[s] = a->seg_scale[s];
+  }
+  p.out = a->out; p.ldo = a->ldo; p.out_off = a->out_off;
+  p.B = a->B; p.heads = a->heads; p.n_q = a->n_q; p.scale = a->softmax_scale;
+  long long rows = static_cast<long long>(a->B) * a->heads * a->n_q;
+  int blocks = static_cast<int>((rows + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == IIR_F32) attn_simt_kernel<float><<<blocks, 256, 0, st>>>(p);
+  else attn_simt_kernel<bf16><<<blocks, 256, 0, st>>>(p);
+  count_launch();
+  return check_launch("iir_attn_simt");
+}
+
+extern "C" int iir_linear_small(const void* x, int x_dtype, const void* w, int w_dtype,
+                                const float* bias, void* out, int out_dtype, int M, int N, int K,
+                                int act, void* stream) {
+  IIR_REQUIRE(x && w && out && M >= 1 && M <= 16 && N > 0 && K > 0,
+              "iir_linear_small: need 1 <= M <= 16 (M=%d)", M);
+  int blocks = (N + 7) / 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define GO(TX, TW, TO)                                                                      \
+  linear_small_kernel<TX, TW, TO><<<blocks, 256, 0, st>>>(                                  \
+      reinterpret_cast<const TX*>(x), reinterpret_cast<const TW*>(w), bias,                 \
+      reinterpret_cast<TO*>(out), M, N, K, act)
+  IIR_REQUIRE(x_dtype == IIR_F32, "iir_linear_small: x must be fp32");
+  if (w_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float, float);
+  else if (w_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(float, bf16, float);
+  else if (w_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, float, bf16);
+  else GO(float, bf16, bf16);
+#undef GO
+  count_launch();
+  return check_launch("iir_linear_small");
+}

@@ -1,0 +1,243 @@
+"""Thin torch-tensor wrappers over the C ABI (one Python function per entry point).
+
+PyTorch is used for device memory and streams only; every function here launches hand-written
+sm_100a kernels from ``libinstantir_b200.so`` on torch's current CUDA stream and raises on any
+failure.  Nothing in this module computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, BF16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype} (fp32 or bf16 only)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.IIRError("instantir_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Optional[torch.Tensor], name: str):
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous fp32 tensor")
+    return t
+
+
+def default_bn(n: int, pair: bool = False) -> int:
+    """N-tile width: 256 when it divides N, else the largest multiple of 32 (64 when paired)
+    <= 256 that divides N; falls back to a masked 128-wide tile."""
+    step = 64 if pair else 32
+    for bn in range(256, step - 1, -step):
+        if n % bn == 0:
+            return bn
+    return 128
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
+         lda: Optional[int] = None, bias=None, rowvec=None, rows_per_sample: int = 0,
+         residual=None, ld_res: Optional[int] = None, aux=None, ld_aux: Optional[int] = None,
+         ld_out: Optional[int] = None, act: int = ACT_NONE, pair: int = PAIR_NONE,
+         bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True):
+    """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1."""
+    lib = _lib.load()
+    n_out = N // 2 if pair else N
+    g = _lib.GemmArgs()
+    g.a, g.w = _p(a), _p(w)
+    g.a_dtype, g.w_dtype = _dt(a), _dt(w)
+    g.M, g.N, g.K = M, N, K
+    g.lda = lda if lda is not None else K
+    if conv is not None:
+        g.conv = 3
+        g.n_img, g.H, g.W, g.Cin = conv["n_img"], conv["H"], conv["W"], conv["Cin"]
+        g.stride = conv.get("stride", 1)
+        g.up2 = conv.get("up2", 0)
+    g.bias = _p(_f32c(bias, "bias"))
+    g.rowvec = _p(_f32c(rowvec, "rowvec"))
+    g.rows_per_sample = rows_per_sample
+    if residual is not None:
+        g.residual, g.res_dtype = _p(residual), _dt(residual)
+        g.ld_res = ld_res if ld_res is not None else n_out
+    if aux is not None:
+        g.aux, g.aux_dtype = _p(aux), _dt(aux)
+        g.ld_aux = ld_aux if ld_aux is not None else n_out
+    g.out, g.out_dtype = _p(out), _dt(out)
+    g.ld_out = ld_out if ld_out is not None else n_out
+    g.act, g.pair = act, pair
+    g.bn = bn if bn is not None else default_bn(N, bool(pair))
+    fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
+    _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt")
+    return out
+
+
+def conv3x3_direct(x, w, bias, out, *, in_nchw: bool, out_nchw: bool, n_img: int, H: int, W: int,
+                   Cin: int, Cout: int, out_H: Optional[int] = None, out_row_off: int = 0):
+    lib = _lib.load()
+    _f32c(w, "w")
+    _f32c(bias, "bias")
+    _lib.check(lib.iir_conv3x3_direct(_p(x), _dt(x), int(in_nchw), _p(w), _p(bias), _p(out), _dt(out),
+                                      int(out_nchw), n_img, H, W, Cin, Cout,
+                                      out_H if out_H is not None else H, out_row_off, _stream()),
+               "iir_conv3x3_direct")
+    return out
+
+
+def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Sequence[int],
+              ldks: Sequence[int], vs: Sequence[torch.Tensor], v_offs: Sequence[int],
+              ldvs: Sequence[int], kv_lens: Sequence[int], seg_scales: Sequence[float], out,
+              out_off: int, ldo: int, *, B: int, heads: int, n_q: int, softmax_scale: float,
+              tc: bool = True):
+    lib = _lib.load()
+    a = _lib.AttnArgs()
+    a.q, a.ldq, a.q_off = _p(q), ldq, q_off
+    a.n_seg = len(ks)
+    for s in range(len(ks)):
+        a.k[s], a.ldk[s], a.k_off[s] = _p(ks[s]), ldks[s], k_offs[s]
+        a.v[s], a.ldv[s], a.v_off[s] = _p(vs[s]), ldvs[s], v_offs[s]
+        a.kv_len[s] = kv_lens[s]
+        a.seg_scale[s] = seg_scales[s]
+    a.out, a.ldo, a.out_off = _p(out), ldo, out_off
+    a.dtype = _dt(q)
+    a.B, a.heads, a.n_q = B, heads, n_q
+    a.softmax_scale = softmax_scale
+    fn = lib.iir_attn_tc if tc else lib.iir_attn_simt
+    _lib.check(fn(C.byref(a), _stream()), "iir_attn_tc" if tc else "iir_attn_simt")
+    return out
+
+
+_gn_scratch = {}
+
+
+def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
+    need = int(_lib.load().iir_groupnorm_scratch_floats(n_img, groups))
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _gn_scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1 << 16), dtype=torch.float32, device=device)
+        _gn_scratch[key] = buf
+    return buf
+
+
+def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int = 32,
+              eps: float = 1e-5, silu: bool = False):
+    lib = _lib.load()
+    part = _gn_partials(x.device, n_img, groups)
+    _lib.check(lib.iir_groupnorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
+                                 _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _p(part),
+                                 _stream()), "iir_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, out, *, rows: int, C: int, eps: float = 1e-5, mod=None,
+              rows_per_sample: int = 0):
+    lib = _lib.load()
+    _lib.check(lib.iir_layernorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
+                                 _p(_f32c(mod, "mod")), rows_per_sample, _p(out), _dt(out), rows, C,
+                                 eps, _stream()), "iir_layernorm")
+    return out
+
+
+def concat_inject(h, C1: int, skip, C2: int, out, *, M: int, rh=None, rs=None, cond_scale=None,
+                  rows_per_sample: int = 0):
+    lib = _lib.load()
+    _lib.check(lib.iir_concat_inject(_p(h), _dt(h), C1, _p(rh), _dt(rh) if rh is not None else 0,
+                                     _p(skip), _dt(skip) if skip is not None else 0, C2, _p(rs),
+                                     _dt(rs) if rs is not None else 0, _p(_f32c(cond_scale, "cond_scale")),
+                                     rows_per_sample, _p(out), _dt(out), M, _stream()),
+               "iir_concat_inject")
+    return out
+
+
+def upsample2x(x, out, *, n_img: int, H: int, W: int, C: int):
+    lib = _lib.load()
+    _lib.check(lib.iir_upsample2x(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
+               "iir_upsample2x")
+    return out
+
+
+def im2col3x3_s2(x, out, *, n_img: int, H: int, W: int, C: int):
+    lib = _lib.load()
+    _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
+               "iir_im2col3x3_s2")
+    return out
+
+
+def cast2d(x, ld_in: int, out, ld_out: int, *, rows: int, cols: int):
+    lib = _lib.load()
+    _lib.check(lib.iir_cast2d(_p(x), _dt(x), ld_in, _p(out), _dt(out), ld_out, rows, cols, _stream()),
+               "iir_cast2d")
+    return out
+
+
+def silu(x, out):
+    lib = _lib.load()
+    _lib.check(lib.iir_silu(_p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream()), "iir_silu")
+    return out
+
+
+def add(a, b, out):
+    lib = _lib.load()
+    _lib.check(lib.iir_add(_p(a), _dt(a), _p(b), _dt(b), _p(out), _dt(out), out.numel(), _stream()),
+               "iir_add")
+    return out
+
+
+def timestep_embedding(t, dim: int, out):
+    lib = _lib.load()
+    _f32c(t, "t")
+    _lib.check(lib.iir_timestep_embedding(_p(t), t.numel(), dim, _p(out), _dt(out), _stream()),
+               "iir_timestep_embedding")
+    return out
+
+
+def linear_small(x, w, bias, out, *, M: int, N: int, K: int, act: int = ACT_NONE):
+    lib = _lib.load()
+    _lib.check(lib.iir_linear_small(_p(x), _dt(x), _p(w), _dt(w), _p(_f32c(bias, "bias")), _p(out),
+                                    _dt(out), M, N, K, act, _stream()), "iir_linear_small")
+    return out
+
+
+def lcm_step(eps, x, out, *, alpha_prod_t: float, c_skip: float, c_out: float):
+    lib = _lib.load()
+    _f32c(x, "x")
+    _f32c(out, "out")
+    _lib.check(lib.iir_lcm_step(_p(eps), _dt(eps), _p(x), _p(out), x.numel(), alpha_prod_t, c_skip,
+                                c_out, _stream()), "iir_lcm_step")
+    return out
+
+
+def cfg_ddpm_step(eps_uncond, eps_cond, x, noise, prev, pred_x0, *, guidance: float,
+                  alpha_prod_t: float, c_x0: float, c_xt: float, sigma: float):
+    lib = _lib.load()
+    _f32c(x, "x")
+    _f32c(noise, "noise")
+    _f32c(prev, "prev")
+    _f32c(pred_x0, "pred_x0")
+    _lib.check(lib.iir_cfg_ddpm_step(_p(eps_uncond), _p(eps_cond), _dt(eps_uncond), _p(x), _p(noise),
+                                     _p(prev), _p(pred_x0), x.numel(), guidance, alpha_prod_t, c_x0,
+                                     c_xt, sigma, _stream()), "iir_cfg_ddpm_step")
+    return prev
+
+
+def add_noise(x0, noise, out, *, alpha_prod_t: float):
+    lib = _lib.load()
+    _lib.check(lib.iir_add_noise(_p(_f32c(x0, "x0")), _p(_f32c(noise, "noise")), _p(_f32c(out, "out")),
+                                 x0.numel(), alpha_prod_t, _stream()), "iir_add_noise")
+    return out

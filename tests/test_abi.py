@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports exactly the
+symbols include/instantir_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+from instantir_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "instantir_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(iir_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_list_agree():
+    assert _header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    lib = _lib.load()
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.iir_abi_version() == 1
+    assert isinstance(lib.iir_launch_count(), int)
+    assert lib.iir_groupnorm_scratch_floats(2, 32) == 2 * 64 * 32 * 2
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors vs the C compiler's own layout of the header structs."""
+    import subprocess
+
+    fields_g = ["a", "M", "lda", "conv", "bias", "rows_per_sample", "residual", "ld_res", "aux", "out",
+                "ld_out", "act", "bn"]
+    fields_a = ["q", "n_seg", "k", "ldk", "k_off", "v", "kv_len", "seg_scale", "out", "dtype", "n_q",
+                "softmax_scale"]
+    prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "instantir_b200.h"', "int main(void){",
+            'printf("%zu %zu\\n", sizeof(iir_gemm_args), sizeof(iir_attn_args));']
+    prog += [f'printf("%zu\\n", offsetof(iir_gemm_args, {f}));' for f in fields_g]
+    prog += [f'printf("%zu\\n", offsetof(iir_attn_args, {f}));' for f in fields_a]
+    prog += ["return 0;}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    nums = [int(x) for x in out]
+    assert nums[0] == ctypes.sizeof(_lib.GemmArgs) and nums[1] == ctypes.sizeof(_lib.AttnArgs)
+    got = [getattr(_lib.GemmArgs, f).offset for f in fields_g] + [getattr(_lib.AttnArgs, f).offset for f in fields_a]
+    assert nums[2:] == got
+
+
+def test_invalid_arguments_are_reported_not_crashed():
+    lib = _lib.load()
+    rc = lib.iir_lcm_step(None, 0, None, None, 7, 0.5, 0.0, 1.0, None)
+    assert rc == -1
+    assert b"iir_lcm_step" in lib.iir_last_error()
+    g = _lib.GemmArgs()
+    g.a_dtype = g.w_dtype = _lib.F32
+    assert lib.iir_gemm_tc(ctypes.byref(g), None) == -1  # fp32 operands are refused by the tc path
+    assert b"bf16" in lib.iir_last_error()

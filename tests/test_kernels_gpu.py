@@ -1,0 +1,356 @@
+"""Per-kernel numerics: every C-ABI entry point against a plain PyTorch fp32 reference of the same
+op (computed on the GPU in fp32 with TF32 disabled).  Tolerances: fp32 kernels 2e-5 relative L2,
+bf16 tensor-core kernels 6e-3 relative L2 (bf16 operand rounding, fp32 accumulation)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from instantir_b200 import ops  # noqa: E402
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def pack_pairs(w, b, bn):
+    """[first | second] halves interleaved per bn-wide tile (GEGLU / SFT weight packing)."""
+    n2 = w.shape[0] // 2
+    half = bn // 2
+    w1, w2 = w[:n2], w[n2:]
+    b1, b2 = b[:n2], b[n2:]
+    ws, bs = [], []
+    for t in range(n2 // half):
+        ws += [w1[t * half:(t + 1) * half], w2[t * half:(t + 1) * half]]
+        bs += [b1[t * half:(t + 1) * half], b2[t * half:(t + 1) * half]]
+    return torch.cat(ws).contiguous(), torch.cat(bs).contiguous()
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 192, 320, 64), (1024, 640, 640, 128),
+                                      (2048, 1280, 1280, 256), (515, 320, 2560, 160)])
+def test_gemm_linear(tc, M, N, K, bn):
+    dt = torch.bfloat16 if tc else torch.float32
+    a = rnd(M, K, seed=1, dtype=dt)
+    w = rnd(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias = rnd(N, seed=3)
+    res = rnd(M, N, seed=4)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, residual=res, bn=bn, tc=tc)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + res
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < (3e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_gemm_bf16_out_silu_rowvec(tc):
+    M, N, K, rps = 512, 256, 192, 128
+    dt = torch.bfloat16 if tc else torch.float32
+    a = rnd(M, K, seed=1, dtype=dt)
+    w = rnd(N, K, seed=2, scale=K ** -0.5, dtype=dt)
+    bias = rnd(N, seed=3)
+    rv = rnd(M // rps, N, seed=5)
+    out = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, rowvec=rv, rows_per_sample=rps, act=ops.ACT_SILU,
+             bn=128, tc=tc)
+    torch.cuda.synchronize()
+    ref = F.silu(a.float() @ w.float().t() + bias + rv.repeat_interleave(rps, 0))
+    assert rel_l2(out, ref) < (6e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_geglu(tc, bn):
+    M, C, K = 384, 256, 128  # proj: K -> 2*C, out C
+    dt = torch.bfloat16 if tc else torch.float32
+    a = rnd(M, K, seed=1, dtype=dt)
+    w = rnd(2 * C, K, seed=2, scale=K ** -0.5, dtype=dt)
+    b = rnd(2 * C, seed=3)
+    wp, bp = pack_pairs(w, b, bn)
+    out = torch.empty(M, C, device=DEV, dtype=dt)
+    ops.gemm(a, wp, out, M=M, N=2 * C, K=K, bias=bp, pair=ops.PAIR_GEGLU, bn=bn, tc=tc)
+    torch.cuda.synchronize()
+    y = a.float() @ w.float().t() + b
+    ref = y[:, :C] * F.gelu(y[:, C:])
+    assert rel_l2(out, ref) < (8e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_gemm_sft_pair(tc):
+    M, C, K, bn = 256, 128, 192, 128
+    dt = torch.bfloat16 if tc else torch.float32
+    a = rnd(M, K, seed=1, dtype=dt)
+    w = rnd(2 * C, K, seed=2, scale=K ** -0.5, dtype=dt)  # rows [gamma | beta]
+    b = rnd(2 * C, seed=3)
+    h = rnd(M, C, seed=6)
+    wp, bp = pack_pairs(w, b, bn)
+    out = torch.empty(M, C, device=DEV, dtype=dt)
+    ops.gemm(a, wp, out, M=M, N=2 * C, K=K, bias=bp, pair=ops.PAIR_SFT, aux=h, bn=bn, tc=tc)
+    torch.cuda.synchronize()
+    y = a.float() @ w.float().t() + b
+    ref = h * (y[:, :C] + 1) + y[:, C:]
+    assert rel_l2(out, ref) < (8e-3 if tc else 2e-5)
+
+
+def _conv_ref(x_nhwc, w_packed, bias, stride=1, up2=False):
+    n, h, w_, c = x_nhwc.shape
+    co = w_packed.shape[0]
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if up2:
+        x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    wt = w_packed.float().view(co, 3, 3, c).permute(0, 3, 1, 2)
+    y = F.conv2d(x, wt, bias, stride=stride, padding=1)
+    return y.permute(0, 2, 3, 1).reshape(-1, co)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("n,H,W,Cin,Cout,bn", [(2, 16, 16, 64, 128, 128), (1, 32, 32, 128, 64, 64),
+                                               (4, 8, 8, 64, 64, 64), (2, 64, 32, 64, 192, 64),
+                                               (1, 8, 128, 64, 64, 64), (3, 8, 8, 128, 128, 128),
+                                               (1, 12, 24, 64, 64, 64)])
+def test_conv3x3(tc, n, H, W, Cin, Cout, bn):
+    dt = torch.bfloat16 if tc else torch.float32
+    x = rnd(n, H, W, Cin, seed=1, dtype=dt)
+    w = rnd(Cout, 9 * Cin, seed=2, scale=(9 * Cin) ** -0.5, dtype=dt)
+    bias = rnd(Cout, seed=3)
+    rv = rnd(n, Cout, seed=4)
+    M = n * H * W
+    out = torch.full((M, Cout), float("nan"), device=DEV, dtype=torch.float32)
+    ops.gemm(x, w, out, M=M, N=Cout, K=9 * Cin, bias=bias, rowvec=rv, rows_per_sample=H * W, bn=bn,
+             conv=dict(n_img=n, H=H, W=W, Cin=Cin), tc=tc)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, bias) + rv.repeat_interleave(H * W, 0)
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < (3e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("stride,up2", [(2, 0), (1, 1)])
+def test_conv3x3_simt_stride_upsample(stride, up2):
+    n, H, W, Cin, Cout = 2, 8, 12, 32, 48
+    x = rnd(n, H, W, Cin, seed=1)
+    w = rnd(Cout, 9 * Cin, seed=2, scale=0.05)
+    bias = rnd(Cout, seed=3)
+    Hin, Win = (2 * H, 2 * W) if up2 else (H, W)
+    Ho, Wo = (Hin - 1) // stride + 1, (Win - 1) // stride + 1
+    M = n * Ho * Wo
+    out = torch.empty(M, Cout, device=DEV)
+    ops.gemm(x, w, out, M=M, N=Cout, K=9 * Cin, bias=bias,
+             conv=dict(n_img=n, H=Hin, W=Win, Cin=Cin, stride=stride, up2=up2), tc=False)
+    torch.cuda.synchronize()
+    assert rel_l2(out, _conv_ref(x, w, bias, stride=stride, up2=bool(up2))) < 2e-5
+
+
+def test_im2col_s2_matches_strided_conv():
+    n, H, W, C, Cout = 2, 16, 16, 64, 64
+    x = rnd(n, H, W, C, seed=1)
+    w = rnd(Cout, 9 * C, seed=2, scale=0.04, dtype=torch.bfloat16)
+    cols = torch.empty(n * (H // 2) * (W // 2), 9 * C, device=DEV, dtype=torch.bfloat16)
+    ops.im2col3x3_s2(x, cols, n_img=n, H=H, W=W, C=C)
+    out = torch.empty(cols.shape[0], Cout, device=DEV)
+    ops.gemm(cols, w, out, M=cols.shape[0], N=Cout, K=9 * C, bn=64, tc=True)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x.to(torch.bfloat16), w, None, stride=2)
+    assert rel_l2(out, ref) < 3e-3
+
+
+def test_conv3x3_direct_layouts():
+    n, H, W, Cin, Cout = 2, 16, 8, 4, 64
+    x = rnd(n, Cin, H, W, seed=1)
+    w = rnd(Cout, 3, 3, Cin, seed=2, scale=0.2)
+    b = rnd(Cout, seed=3)
+    canvas = torch.zeros(n, 2 * H, W, Cout, device=DEV)
+    ops.conv3x3_direct(x, w, b, canvas, in_nchw=True, out_nchw=False, n_img=n, H=H, W=W, Cin=Cin,
+                       Cout=Cout, out_H=2 * H, out_row_off=H)
+    ref = F.conv2d(x, w.permute(0, 3, 1, 2), b, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(canvas[:, H:], ref) < 2e-5 and float(canvas[:, :H].abs().max()) == 0.0
+    # NHWC bf16 in -> NCHW fp32 out (conv_out)
+    xh = rnd(n, H, W, 64, seed=5, dtype=torch.bfloat16)
+    w2 = rnd(4, 3, 3, 64, seed=6, scale=0.05)
+    b2 = rnd(4, seed=7)
+    o2 = torch.empty(n, 4, H, W, device=DEV)
+    ops.conv3x3_direct(xh, w2, b2, o2, in_nchw=False, out_nchw=True, n_img=n, H=H, W=W, Cin=64, Cout=4)
+    torch.cuda.synchronize()
+    ref2 = F.conv2d(xh.float().permute(0, 3, 1, 2), w2.permute(0, 3, 1, 2), b2, padding=1)
+    assert rel_l2(o2, ref2) < 2e-5
+
+
+# ------------------------------------------------------------------------------- attention
+def _sdpa_ref(q, k, v, heads, scale):
+    B, n, C = q.shape
+    d = C // heads
+    qh = q.float().view(B, n, heads, d).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, n, C)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("B,heads,n", [(1, 1, 128), (2, 2, 256), (2, 4, 320), (1, 2, 1024), (2, 1, 64)])
+def test_self_attention_fused_qkv(tc, B, heads, n):
+    C = heads * 64
+    dt = torch.bfloat16 if tc else torch.float32
+    qkv = rnd(B, n, 3 * C, seed=1, dtype=dt)
+    out = torch.full((B, n, C), float("nan"), device=DEV, dtype=dt)
+    ops.attention(qkv, 0, 3 * C, [qkv], [C], [3 * C], [qkv], [2 * C], [3 * C], [n], [1.0], out, 0, C,
+                  B=B, heads=heads, n_q=n, softmax_scale=0.125, tc=tc)
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < (8e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_decoupled_cross_attention_two_segments(tc):
+    B, heads, n, nt, ni, scale_ip = 2, 2, 256, 77, 64, 0.7
+    C = heads * 64
+    dt = torch.bfloat16 if tc else torch.float32
+    q = rnd(B, n, C, seed=1, dtype=dt)
+    kvt = rnd(B, nt, 2 * C, seed=2, dtype=dt)
+    ki = rnd(B, ni, C, seed=3, dtype=dt)
+    vi = rnd(B, ni, C, seed=4, dtype=dt)
+    out = torch.empty(B, n, C, device=DEV, dtype=dt)
+    ops.attention(q, 0, C, [kvt, ki], [0, 0], [2 * C, C], [kvt, vi], [C, 0], [2 * C, C], [nt, ni],
+                  [1.0, scale_ip], out, 0, C, B=B, heads=heads, n_q=n, softmax_scale=0.125, tc=tc)
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(q, kvt[..., :C], kvt[..., C:], heads, 0.125) + scale_ip * _sdpa_ref(q, ki, vi, heads, 0.125)
+    assert rel_l2(out, ref) < (8e-3 if tc else 2e-5)
+
+
+# ----------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("xdt,odt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("n,HW,C,silu", [(2, 256, 64, True), (2, 1024, 320, True), (1, 4096, 1920, False),
+                                         (3, 64, 2560, True)])
+def test_groupnorm(xdt, odt, n, HW, C, silu):
+    x = (rnd(n, HW, C, seed=1) * 2 + 0.5).to(xdt)
+    g, b = rnd(C, seed=2), rnd(C, seed=3)
+    out = torch.empty(n, HW, C, device=DEV, dtype=odt)
+    ops.groupnorm(x, g, b, out, n_img=n, HW=HW, C=C, eps=1e-5, silu=silu)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(out, ref) < (5e-3 if odt == torch.bfloat16 else 2e-5)
+
+
+@pytest.mark.parametrize("C", [64, 640, 1280, 2048])
+def test_layernorm_affine_and_adaln(C):
+    rows, rps = 96, 48
+    x = rnd(rows, C, seed=1) * 3 + 1
+    g, b = rnd(C, seed=2), rnd(C, seed=3)
+    out = torch.empty(rows, C, device=DEV)
+    ops.layernorm(x, g, b, out, rows=rows, C=C, eps=1e-5)
+    torch.cuda.synchronize()
+    assert rel_l2(out, F.layer_norm(x, (C,), g, b, 1e-5)) < 2e-5
+    mod = rnd(rows // rps, 2 * C, seed=4) * 0.3
+    ops.layernorm(x, None, None, out, rows=rows, C=C, eps=1e-6, mod=mod, rows_per_sample=rps)
+    torch.cuda.synchronize()
+    m = mod.repeat_interleave(rps, 0)
+    ref = F.layer_norm(x, (C,), None, None, 1e-6) * (1 + m[:, C:]) + m[:, :C]
+    assert rel_l2(out, ref) < 2e-5
+
+
+# ----------------------------------------------------------------------- movement / small
+def test_concat_inject_and_plain_add():
+    M, C1, C2, rps = 512, 128, 64, 256
+    h, sk = rnd(M, C1, seed=1), rnd(M, C2, seed=2)
+    rh, rs = rnd(M, C1, seed=3, dtype=torch.bfloat16), rnd(M, C2, seed=4, dtype=torch.bfloat16)
+    cs = torch.tensor([0.0, 1.0], device=DEV)
+    out = torch.empty(M, C1 + C2, device=DEV, dtype=torch.bfloat16)
+    ops.concat_inject(h, C1, sk, C2, out, M=M, rh=rh, rs=rs, cond_scale=cs, rows_per_sample=rps)
+    torch.cuda.synchronize()
+    s = cs.repeat_interleave(rps)[:, None]
+    ref = torch.cat([h + s * rh.float(), sk + s * rs.float()], 1)
+    assert rel_l2(out, ref) < 4e-3
+    out2 = torch.empty(M, C1, device=DEV)
+    ops.concat_inject(h, C1, None, 0, out2, M=M, rh=rh, cond_scale=cs, rows_per_sample=rps)
+    torch.cuda.synchronize()
+    assert rel_l2(out2, h + s * rh.float()) < 1e-6
+
+
+def test_upsample_cast_silu_add_timestep():
+    n, H, W, C = 2, 8, 4, 64
+    x = rnd(n, H, W, C, seed=1)
+    up = torch.empty(n, 2 * H, 2 * W, C, device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x(x, up, n_img=n, H=H, W=W, C=C)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(up, ref) < 4e-3
+    src = rnd(64, 256, seed=2)
+    dst = torch.zeros(64, 128, device=DEV, dtype=torch.bfloat16)
+    ops.cast2d(src[:, 64:], 256, dst, 128, rows=64, cols=128)
+    torch.cuda.synchronize()
+    assert rel_l2(dst, src[:, 64:192]) < 4e-3
+    y = torch.empty_like(src)
+    ops.silu(src, y)
+    z = torch.empty_like(src)
+    ops.add(src, y, z)
+    torch.cuda.synchronize()
+    assert rel_l2(y, F.silu(src)) < 1e-6 and rel_l2(z, src + F.silu(src)) < 1e-6
+    t = torch.tensor([958.0, 501.0, 1.0, 1024.0], device=DEV)
+    emb = torch.empty(4, 320, device=DEV)
+    ops.timestep_embedding(t, 320, emb)
+    torch.cuda.synchronize()
+    half = 160
+    freq = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    arg = t[:, None] * freq[None]
+    assert rel_l2(emb, torch.cat([arg.cos(), arg.sin()], -1)) < 1e-5
+
+
+@pytest.mark.parametrize("wdt", [torch.float32, torch.bfloat16])
+def test_linear_small(wdt):
+    M, N, K = 2, 2560, 1280
+    x = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5, dtype=wdt)
+    b = rnd(N, seed=3)
+    out = torch.empty(M, N, device=DEV)
+    ops.linear_small(x, w, b, out, M=M, N=N, K=K, act=ops.ACT_SILU)
+    torch.cuda.synchronize()
+    assert rel_l2(out, F.silu(x @ w.float().t() + b)) < 2e-5
+
+
+# ------------------------------------------------------------------------------- scheduler
+def test_scheduler_kernels():
+    n = 2 * 4 * 32 * 32
+    eps_u, eps_c, x, z = (rnd(n, seed=s) for s in (1, 2, 3, 4))
+    abar, c_skip, c_out = 0.0075347, 2.7e-9, 0.99999
+    out = torch.empty(n, device=DEV)
+    ops.lcm_step(eps_c, x, out, alpha_prod_t=abar, c_skip=c_skip, c_out=c_out)
+    x0 = (x - math.sqrt(1 - abar) * eps_c) / math.sqrt(abar)
+    torch.cuda.synchronize()
+    assert rel_l2(out, c_out * x0 + c_skip * x) < 1e-6
+    prev, px0 = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    g, c0, c1, sig = 7.0, 0.031, 0.84, 0.52
+    ops.cfg_ddpm_step(eps_u, eps_c, x, z, prev, px0, guidance=g, alpha_prod_t=abar, c_x0=c0, c_xt=c1,
+                      sigma=sig)
+    e = eps_u + g * (eps_c - eps_u)
+    x0 = (x - math.sqrt(1 - abar) * e) / math.sqrt(abar)
+    torch.cuda.synchronize()
+    assert rel_l2(px0, x0) < 1e-6 and rel_l2(prev, c0 * x0 + c1 * x + sig * z) < 1e-6
+    ops.add_noise(x, z, out, alpha_prod_t=abar)
+    torch.cuda.synchronize()
+    assert rel_l2(out, math.sqrt(abar) * x + math.sqrt(1 - abar) * z) < 1e-6
+
+
+def test_no_cpu_fallback():
+    from instantir_b200._lib import IIRError
+
+    with pytest.raises(IIRError):
+        ops.silu(torch.zeros(8), torch.zeros(8))

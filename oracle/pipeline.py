@@ -1,0 +1,105 @@
+"""Oracle denoising loop — restates pipelines/sdxl_instantir.py:1385-1666 (CPU fp32).
+
+Inputs are already-encoded tensors (text/pooled/DINOv2 embeddings, LQ latent): the once-per-image
+encoders are outside the hot path.  Quirks of the reference loop are kept:
+the `(cond_scale>0.1).sum().item() > 0` gate (:1542), stale residuals multiplied by zero after
+control ends (:1602-1603), the duplicate temb computation (:1516-1529).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+
+def step_masks(n_steps, preview_start, preview_end, control_guidance_start, control_guidance_end):
+    """controlnet_keep / previewing — pipelines/sdxl_instantir.py:1415-1421."""
+    keep, prev = [], []
+    for i in range(n_steps):
+        keep.append(1.0 - float(i / n_steps < control_guidance_start or (i + 1) / n_steps > control_guidance_end))
+        prev.append(1.0 - float(i / n_steps < preview_start or (i + 1) / n_steps > preview_end))
+    return keep, prev
+
+
+@torch.no_grad()
+def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, prompt_embeds,
+                    negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
+                    ip_image_embeds, add_time_ids, num_inference_steps=30, guidance_scale=7.0,
+                    preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
+                    controlnet_conditioning_scale=1.0, generator=None, init_latents_with_lq=True,
+                    timesteps=None, record: Optional[dict] = None):
+    """Returns the final latents [B,4,h,w]; `record` (if given) collects per-step tensors.
+
+    image: LQ latent [B,4,h,w] (the reference accepts 4-channel tensors as latents, :1370-1382).
+    ip_image_embeds: [2,B,S,D] stacked (negative, positive) DINOv2 tokens (:700-706).
+    """
+    do_cfg = guidance_scale > 1.0
+    B = image.shape[0]
+    scheduler.set_timesteps(num_inference_steps, timesteps=timesteps)
+    ts = scheduler.timesteps
+    n = len(ts)
+    if init_latents_with_lq:  # init_latents (:931-939): noise drawn first from the user generator
+        noise = torch.randn(image.shape, generator=generator, dtype=image.dtype)
+        latents = scheduler_add_noise(scheduler, image, noise, ts[0])
+    else:
+        latents = torch.randn(image.shape, generator=generator, dtype=image.dtype) * scheduler.init_noise_sigma
+    keep, previewing = step_masks(n, preview_start, preview_end, control_guidance_start, control_guidance_end)
+    scales = controlnet_conditioning_scale if isinstance(controlnet_conditioning_scale, list) else [controlnet_conditioning_scale] * n
+    add_text_embeds = pooled_prompt_embeds
+    time_ids = add_time_ids
+    if do_cfg:
+        prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
+        add_text_embeds = torch.cat([negative_pooled_prompt_embeds, add_text_embeds], dim=0)
+        time_ids = torch.cat([time_ids, time_ids], dim=0)
+        image = torch.cat([image] * 2, dim=0)
+        image_embeds = [torch.cat([ip_image_embeds[0], ip_image_embeds[1]], dim=0).unsqueeze(1)]
+    else:
+        image_embeds = [ip_image_embeds[1].unsqueeze(1)]
+    preview_factor = torch.ones((latents.shape[0], 1, 1, 1), dtype=latents.dtype)
+    down_res = mid_res = None
+    for i, t in enumerate(ts):
+        x_in = torch.cat([latents] * 2) if do_cfg else latents
+        x_in = scheduler.scale_model_input(x_in, t)
+        added = {"text_embeds": add_text_embeds, "time_ids": time_ids, "image_embeds": image_embeds}
+        emb = unet.time_embedding(unet.get_time_embed(sample=x_in, timestep=t))
+        emb = emb + unet.get_aug_embed(emb=emb, encoder_hidden_states=prompt_embeds, added_cond_kwargs=added)
+        ca_kwargs = {"temb": emb}
+        cond_scale = preview_factor.clamp(0.0, scales[i]) * keep[i]
+        cond_scale = torch.cat([cond_scale] * 2) if do_cfg else cond_scale
+        preview_latent = None
+        if (cond_scale > 0.1).sum().item() > 0:
+            if previewing[i] > 0:
+                unet.enable_adapters()
+                preview_noise = unet(x_in, t, encoder_hidden_states=prompt_embeds, cross_attention_kwargs=ca_kwargs,
+                                     added_cond_kwargs=added, return_dict=False)[0]
+                preview_latent = previewer_scheduler.step(preview_noise, t.to(dtype=torch.int64), x_in,
+                                                          return_dict=False)[0]
+                unet.disable_adapters()
+            else:
+                preview_latent = image
+            down_res, mid_res = aggregator(image, t, encoder_hidden_states=prompt_embeds,
+                                           controlnet_cond=preview_latent,
+                                           added_cond_kwargs={"text_embeds": add_text_embeds, "time_ids": time_ids},
+                                           return_dict=False)
+        down_scaled = [s * cond_scale for s in down_res]
+        mid_scaled = mid_res * cond_scale
+        noise_pred = unet(x_in, t, encoder_hidden_states=prompt_embeds, cross_attention_kwargs=ca_kwargs,
+                          down_block_additional_residuals=down_scaled, mid_block_additional_residual=mid_scaled,
+                          added_cond_kwargs=added, return_dict=False)[0]
+        if do_cfg:
+            e_u, e_c = noise_pred.chunk(2)
+            noise_pred = e_u + guidance_scale * (e_c - e_u)
+        out = scheduler.step(noise_pred, t, latents, generator=generator, return_dict=True)
+        latents = out.prev_sample
+        if record is not None:
+            record.setdefault("latents", []).append(latents.clone())
+            record.setdefault("pred_x0", []).append(out.pred_original_sample.clone())
+            record.setdefault("noise_pred", []).append(noise_pred.clone())
+            record.setdefault("preview", []).append(None if preview_latent is None else preview_latent.clone())
+    return latents
+
+
+def scheduler_add_noise(scheduler, x0, noise, t):
+    ac = scheduler.alphas_cumprod.to(dtype=x0.dtype)
+    t = int(t)
+    return ac[t] ** 0.5 * x0 + (1 - ac[t]) ** 0.5 * noise

@@ -1,0 +1,156 @@
+"""Pins the CPU oracle to the reference: replays it against vectors produced by running the
+reference's own files verbatim (tests/golden/make_golden.py).  fp32 on CPU; differences are
+summation-order only, so the bar is 2e-5 relative L2 (bit-exact where the op order is identical)."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+from seeding import checksum, seeded_init  # noqa: E402
+
+from oracle import config as ocfg  # noqa: E402
+from oracle import model as om  # noqa: E402
+from oracle import schedulers as osched  # noqa: E402
+
+G = os.path.join(HERE, "golden")
+torch.set_grad_enabled(False)
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def same_weights(module, want):
+    assert abs(checksum(module) - want) <= 1e-9 * max(1.0, abs(want)), "seeded init drifted from the fixture"
+
+
+def test_processors_match_reference_run():
+    g = torch.load(os.path.join(G, "processors.pt"))
+    d = g["dims"]
+    attn = seeded_init(om.Attention(d["C"], d["heads"], d["xdim"]), g["seeds"]["attn"])
+    proc = seeded_init(om.TA_IPAttnProcessor2_0(d["C"], d["xdim"], time_embedding_dim=d["tdim"], scale=d["scale"],
+                                                num_tokens=d["ntok"]), g["seeds"]["proc"])
+    same_weights(attn, g["checksums"]["attn"])
+    same_weights(proc, g["checksums"]["proc"])
+    out = proc(attn, g["hs"], encoder_hidden_states=(g["text"], [g["ip"]]), temb=g["temb"])
+    assert rel(out, g["out_tuple"]) < 2e-6
+    out = proc(attn, g["hs"], encoder_hidden_states=torch.cat([g["text"], g["ip"]], 1), temb=g["temb"])
+    assert rel(out, g["out_concat"]) < 2e-6
+    sa = seeded_init(om.Attention(d["C"], d["heads"]), g["seeds"]["self_attn"])
+    assert rel(om.AttnProcessor2_0()(sa, g["hs"], temb=g["temb"]), g["out_self"]) < 2e-6
+    ada = seeded_init(om.AdaLayerNorm(d["C"], d["tdim"]), g["seeds"]["ada"])
+    assert rel(ada(g["hs"], g["temb"]), g["out_ada"]) < 2e-6
+
+
+def test_resampler_matches_reference_run():
+    g = torch.load(os.path.join(G, "resampler.pt"))
+    rs = seeded_init(om.Resampler(dim=128, depth=2, dim_head=64, heads=2, num_queries=16, embedding_dim=64,
+                                  output_dim=256, ff_mult=4), g["seed"])
+    same_weights(rs, g["checksum"])
+    out = om.MultiIPAdapterImageProjection([rs])([g["x"]])[0]
+    assert out.shape == g["out"].shape and rel(out, g["out"]) < 2e-6
+
+
+def test_lcm_scheduler_matches_reference_run():
+    g = torch.load(os.path.join(G, "lcm_scheduler.pt"))
+    lcm = osched.LCMSingleStepScheduler()
+    assert torch.equal(lcm.alphas_cumprod, g["alphas_cumprod"])
+    for t, want in g["steps"].items():
+        got = lcm.step(g["eps"], torch.tensor(t, dtype=torch.int64), g["x"], return_dict=False)[0]
+        assert got.dtype == torch.float32 and torch.equal(got, want), t
+    assert torch.equal(lcm.add_noise(g["x"], g["eps"], torch.tensor([958, 1])), g["noisy"])
+    # closed forms quoted in SURVEY §8c (vi)
+    assert torch.equal(lcm.step(g["eps"], torch.tensor(0), g["x"], return_dict=False)[0], g["steps"][0])
+    c_skip, _ = lcm.get_scalings_for_boundary_condition_discrete(torch.tensor(1))
+    assert abs(float(c_skip) - 2.494e-3) < 1e-5
+    for i, v in ((0, 0.99914998), (1, 0.99829602), (958, 0.00753477)):
+        assert abs(float(lcm.alphas_cumprod[i]) - v) < 1e-7
+
+
+def _min_sdxl_cfg():
+    # widths of the reference-block UNet assembled in make_golden.py (temb 1280 / text 2048 are
+    # hard-coded in module/min_sdxl.py:249,538)
+    return ocfg.StepConfig(block_out_channels=(64, 128, 256), transformer_layers_per_block=(1, 1, 2),
+                           num_attention_heads=(1, 2, 4), cross_attention_dim=2048, addition_time_embed_dim=32,
+                           pooled_dim=64, time_embed_dim=1280)
+
+
+def test_unet_base_mode_matches_reference_min_sdxl():
+    g = torch.load(os.path.join(G, "min_sdxl.pt"))
+    unet = om.UNet2DConditionModel(_min_sdxl_cfg())
+    assert sorted(k for k, _ in unet.named_parameters()) == g["names"]
+    assert sum(p.numel() for p in unet.parameters()) == g["n_params"]
+    seeded_init(unet, g["seeds"]["unet"])
+    same_weights(unet, g["checksums"]["unet"])
+    out = unet(g["sample"], torch.tensor(g["t"]), g["text"],
+               added_cond_kwargs={"text_embeds": g["pooled"], "time_ids": g["time_ids"]})[0]
+    assert rel(out, g["unet_out"]) < 2e-5
+
+
+def test_resnet_and_transformer_blocks_match_reference():
+    g = torch.load(os.path.join(G, "min_sdxl.pt"))
+    res = seeded_init(om.ResnetBlock2D(96, 64, 1280), g["seeds"]["res"])
+    same_weights(res, g["checksums"]["res"])
+    assert rel(res(g["res_x"], g["res_temb"]), g["res_out"]) < 2e-6
+    t2d = seeded_init(om.Transformer2DModel(128, 2, 1, 2048), g["seeds"]["t2d"])
+    same_weights(t2d, g["checksums"]["t2d"])
+    assert rel(t2d(g["t2d_x"], g["t2d_text"]), g["t2d_out"]) < 2e-5
+
+
+def test_aggregator_matches_reference_forward():
+    g = torch.load(os.path.join(G, "aggregator.pt"))
+    cfg = ocfg.StepConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    agg = om.Aggregator(cfg)
+    om.remove_attn2(agg)
+    assert sorted(k for k, _ in agg.named_parameters()) == g["names"]
+    seeded_init(agg, g["seed"])
+    same_weights(agg, g["checksum"])
+    i = g["inputs"]
+    down, mid = agg(i["sample"], torch.tensor(i["t"]), None, controlnet_cond=i["cond"],
+                    added_cond_kwargs={"text_embeds": i["pooled"], "time_ids": i["time_ids"]})
+    assert len(down) == 9 == len(g["down"])
+    for a, b in zip(down, g["down"]):
+        assert a.shape == b.shape and rel(a, b) < 2e-5
+    assert rel(mid, g["mid"]) < 2e-5
+
+
+def test_structural_invariants_from_survey():
+    """SURVEY §8c derived known answers: parameter counts of the full-size architecture (meta
+    tensors, no memory), from_unet zero residuals, adaLN zero-init == LN."""
+    cfg = ocfg.sdxl()
+    with torch.device("meta"):
+        unet = om.UNet2DConditionModel(cfg)
+        agg = om.Aggregator(cfg)
+        om.remove_attn2(agg)
+        rs = om.make_resampler(cfg)
+    assert sum(p.numel() for p in unet.parameters()) == 2_567_463_684
+    assert sum(p.numel() for p in agg.parameters()) == 1_004_809_280
+    assert sum(p.numel() for p in rs.parameters()) == 82_695_424
+    with torch.device("meta"):
+        om.load_adapter(unet)
+    ip = sum(p.numel() for n, p in unet.named_parameters() if "to_k_ip" in n or "to_v_ip" in n)
+    ada = sum(p.numel() for n, p in unet.named_parameters() if "ln_k_ip" in n or "ln_v_ip" in n)
+    assert ip == 340_787_200 and ada == 426_316_800
+    x, t = torch.randn(2, 5, 64), torch.randn(2, 32)
+    ln = om.AdaLayerNorm(64, 32)
+    assert torch.equal(ln(x, t), torch.nn.functional.layer_norm(x, (64,), eps=1e-6))
+
+
+def test_ddpm_schedule_and_closed_forms():
+    s = osched.DDPMScheduler()
+    s.set_timesteps(30)
+    ts = s.timesteps.tolist()
+    assert ts[0] == 958 and ts[1] == 925 and ts[-2] == 34 and ts[-1] == 1 and len(ts) == 30
+    assert int(s.previous_timestep(torch.tensor(958))) == 925
+    s.set_timesteps(2)
+    assert s.timesteps.tolist() == [501, 1]
+    eps, x = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
+    out = s.step(eps, torch.tensor(1), x, noise=torch.zeros_like(x))
+    a1 = s.alphas_cumprod[1]
+    # t=1 -> prev_t = -499 < 0 -> alpha_prev = 1: prev_sample == pred_original_sample
+    assert rel(out.prev_sample, (x - (1 - a1) ** 0.5 * eps) / a1 ** 0.5) < 1e-6
+    assert rel(out.prev_sample, out.pred_original_sample) < 1e-6

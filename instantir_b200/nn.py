@@ -1,0 +1,279 @@
+"""Building blocks of the host-side executor: light Python objects that mirror the reference's
+module tree, hold weights pre-packed for the sm_100a kernels, and launch those kernels.
+
+Data layout: activations are NHWC / token-major ``[n_img*H*W, C]``.
+In ``bf16`` precision GEMM operands (outputs of norms, attention, GEGLU) are bf16 while the
+*residual stream* (resnet outputs, transformer hidden states, skips) stays fp32 so that rounding
+does not accumulate over the 200+ residual adds of a forward; ``fp32`` precision is the north
+star's check mode (everything fp32, SIMT kernels).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .weights import merge_lora
+
+
+class Runtime:
+    """Execution mode shared by every layer of a model."""
+
+    def __init__(self, device, precision: str = "bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05 path) or 'fp32' (check mode)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ops._lib.IIRError("instantir_b200 runs on CUDA only; there is no CPU fallback")
+        self.precision = precision
+        self.tc = precision == "bf16"
+        self.act_dtype = torch.bfloat16 if self.tc else torch.float32
+        self.w_dtype = self.act_dtype
+        self.lora_enabled = False
+
+    def empty(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.device, dtype=dtype or self.act_dtype)
+
+    def stream(self, *shape):
+        return torch.empty(*shape, device=self.device, dtype=torch.float32)
+
+
+@dataclass
+class FMap:
+    """NHWC feature map: t is [n*H*W, C] contiguous."""
+
+    t: torch.Tensor
+    n: int
+    H: int
+    W: int
+    C: int
+
+    @property
+    def M(self):
+        return self.n * self.H * self.W
+
+    def nchw(self):
+        """zero-copy logical NCHW view (channels_last memory) for reference-shaped returns."""
+        return self.t.view(self.n, self.H, self.W, self.C).permute(0, 3, 1, 2)
+
+
+def fmap_from_nchw(x: torch.Tensor, dtype=None) -> FMap:
+    """accept a reference-style [n,C,H,W] tensor; zero-copy when it is already channels_last."""
+    n, c, h, w = x.shape
+    t = x.permute(0, 2, 3, 1)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return FMap(t.reshape(n * h * w, c), n, h, w, c)
+
+
+class _Packed:
+    """weight (+ optional LoRA-merged twin) selected by rt.lora_enabled."""
+
+    def __init__(self, rt: Runtime, base: torch.Tensor, lora: Optional[torch.Tensor] = None):
+        self.rt, self.base, self.lora = rt, base, lora
+
+    def get(self):
+        return self.lora if (self.rt.lora_enabled and self.lora is not None) else self.base
+
+
+def _pack_pairs(w1, w2, bn):
+    """interleave two [N,K] (or [N]) tensors per bn-wide output tile: [w1 half | w2 half]."""
+    half = bn // 2
+    n = w1.shape[0]
+    assert n % half == 0
+    a = w1.reshape(n // half, half, *w1.shape[1:])
+    b = w2.reshape(n // half, half, *w2.shape[1:])
+    return torch.cat([a, b], dim=1).reshape(2 * n, *w1.shape[1:]).contiguous()
+
+
+def _conv_to_gemm(w):  # [Co,Ci,k,k] -> [Co, k*k*Ci] tap-major
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def _load_w(rt, src, name, transform=None, lora_ok=True):
+    """returns _Packed of the (transformed) weight in rt.w_dtype; merges LoRA when the source has it."""
+    w = src.get(name + ".weight")
+    tw = transform(w) if transform else w
+    base = tw.to(rt.w_dtype).contiguous()
+    lw = None
+    lo = src.get_lora(name) if lora_ok else None
+    if lo is not None:
+        m = merge_lora(w, lo)
+        lw = (transform(m) if transform else m).to(rt.w_dtype).contiguous()
+    return _Packed(rt, base, lw)
+
+
+def _bias(src, name):
+    return src.get(name + ".bias").contiguous() if src.has(name + ".bias") else None
+
+
+class Linear:
+    """nn.Linear on [M,K] activations (module/min_sdxl.py:301-307 etc.) with fused epilogues."""
+
+    def __init__(self, rt, src, name, bias=True):
+        self.rt = rt
+        self.w = _load_w(rt, src, name)
+        self.b = _bias(src, name) if bias else None
+        self.N, self.K = self.w.base.shape
+
+    def __call__(self, a, M, out=None, out_dtype=None, residual=None, act=ops.ACT_NONE):
+        rt = self.rt
+        if out is None:
+            out = torch.empty(M, self.N, device=rt.device, dtype=out_dtype or rt.act_dtype)
+        ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.b, residual=residual, act=act, tc=rt.tc)
+        return out
+
+
+class SmallLinear:
+    """M <= 16 linear on fp32 vectors (time/add embeddings, time_emb_proj, adaLN)."""
+
+    def __init__(self, rt, src, name):
+        self.rt = rt
+        self.w = _load_w(rt, src, name)
+        self.b = _bias(src, name)
+        self.N, self.K = self.w.base.shape
+
+    def __call__(self, x, act=ops.ACT_NONE):
+        M = x.shape[0]
+        out = torch.empty(M, self.N, device=self.rt.device, dtype=torch.float32)
+        for m0 in range(0, M, 16):
+            m1 = min(M, m0 + 16)
+            ops.linear_small(x[m0:m1], self.w.get(), self.b, out[m0:m1], M=m1 - m0, N=self.N, K=self.K, act=act)
+        return out
+
+
+class Conv3x3:
+    """3x3 pad-1 convolution as implicit GEMM (module/min_sdxl.py:246-260,601-618)."""
+
+    def __init__(self, rt, src, name, stride=1):
+        self.rt, self.stride = rt, stride
+        self.w = _load_w(rt, src, name, _conv_to_gemm)
+        self.b = _bias(src, name)
+        self.Cout = self.w.base.shape[0]
+        self.Cin = self.w.base.shape[1] // 9
+
+    def __call__(self, x: FMap, out_dtype=None, rowvec=None, residual=None, act=ops.ACT_NONE, up2=False) -> FMap:
+        rt = self.rt
+        H, W = (2 * x.H, 2 * x.W) if up2 else (x.H, x.W)
+        Ho, Wo = (H - 1) // self.stride + 1, (W - 1) // self.stride + 1
+        M = x.n * Ho * Wo
+        out = torch.empty(M, self.Cout, device=rt.device, dtype=out_dtype or rt.act_dtype)
+        kw = dict(M=M, N=self.Cout, K=9 * self.Cin, bias=self.b, rowvec=rowvec, rows_per_sample=Ho * Wo,
+                  residual=residual, act=act)
+        if not rt.tc:
+            ops.gemm(x.t, self.w.get(), out, conv=dict(n_img=x.n, H=H, W=W, Cin=self.Cin, stride=self.stride, up2=int(up2)),
+                     tc=False, **kw)
+        else:
+            src = x
+            if up2:  # nearest-2x then conv (module/min_sdxl.py:617-618)
+                up = rt.empty(x.n * H * W, x.C)
+                ops.upsample2x(x.t, up, n_img=x.n, H=x.H, W=x.W, C=x.C)
+                src = FMap(up, x.n, H, W, x.C)
+            elif x.t.dtype != rt.act_dtype or self.stride != 1:
+                pass
+            if self.stride == 2:
+                cols = rt.empty(M, 9 * self.Cin)
+                ops.im2col3x3_s2(src.t, cols, n_img=x.n, H=H, W=W, C=self.Cin)
+                ops.gemm(cols, self.w.get(), out, tc=True, **kw)
+            else:
+                a = src.t
+                if a.dtype != rt.act_dtype:
+                    a = rt.empty(src.M, src.C)
+                    ops.cast2d(src.t, src.C, a, src.C, rows=src.M, cols=src.C)
+                ops.gemm(a, self.w.get(), out, conv=dict(n_img=x.n, H=H, W=W, Cin=self.Cin), tc=True, **kw)
+        return FMap(out, x.n, Ho, Wo, self.Cout)
+
+
+class GroupNorm:
+    def __init__(self, rt, src, name, C, groups, eps):
+        self.rt, self.C, self.groups, self.eps = rt, C, groups, eps
+        self.g, self.b = src.get(name + ".weight").contiguous(), src.get(name + ".bias").contiguous()
+
+    def __call__(self, x: FMap, silu: bool) -> FMap:
+        out = self.rt.empty(x.M, x.C)
+        ops.groupnorm(x.t, self.g, self.b, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups, eps=self.eps, silu=silu)
+        return FMap(out, x.n, x.H, x.W, x.C)
+
+
+class LayerNorm:
+    def __init__(self, rt, src, name, C, eps=1e-5):
+        self.rt, self.C, self.eps = rt, C, eps
+        self.g, self.b = src.get(name + ".weight").contiguous(), src.get(name + ".bias").contiguous()
+
+    def __call__(self, x, rows, out_dtype=None):
+        out = torch.empty(rows, self.C, device=self.rt.device, dtype=out_dtype or self.rt.act_dtype)
+        ops.layernorm(x, self.g, self.b, out, rows=rows, C=self.C, eps=self.eps)
+        return out
+
+
+class ResnetBlock2D:
+    """module/min_sdxl.py:242-283.  Kernel plan: GN+SiLU -> conv1 (+bias +temb row-vector in the
+    epilogue) -> GN+SiLU -> conv2 (+bias +residual in the epilogue); the 1x1 shortcut is a GEMM
+    whose fp32 output is that residual."""
+
+    def __init__(self, rt, src, p, cfg, c_in, c_out):
+        self.rt, self.c_in, self.c_out = rt, c_in, c_out
+        self.norm1 = GroupNorm(rt, src, p + ".norm1", c_in, cfg.norm_num_groups, cfg.norm_eps)
+        self.conv1 = Conv3x3(rt, src, p + ".conv1")
+        self.time_emb_proj = SmallLinear(rt, src, p + ".time_emb_proj")
+        self.norm2 = GroupNorm(rt, src, p + ".norm2", c_out, cfg.norm_num_groups, cfg.norm_eps)
+        self.conv2 = Conv3x3(rt, src, p + ".conv2")
+        self.conv_shortcut = None
+        if c_in != c_out:
+            self.conv_shortcut = Linear(rt, _ShortcutSrc(src), p + ".conv_shortcut")
+
+    def __call__(self, x: FMap, temb_act: torch.Tensor) -> FMap:
+        """x: fp32 stream (or act-dtype concat); temb_act = silu(emb) [n, T] fp32."""
+        rt = self.rt
+        h = self.conv1(self.norm1(x, silu=True), rowvec=self.time_emb_proj(temb_act))
+        h = self.norm2(h, silu=True)
+        if self.conv_shortcut is not None:
+            a = x.t
+            if a.dtype != rt.act_dtype:
+                a = rt.empty(x.M, x.C)
+                ops.cast2d(x.t, x.C, a, x.C, rows=x.M, cols=x.C)
+            res = self.conv_shortcut(a, x.M, out_dtype=torch.float32)
+        else:
+            res = x.t
+        return self.conv2(h, out_dtype=torch.float32, residual=res)
+
+
+class _ShortcutSrc:
+    """view of a source that hands a 1x1 conv weight [Co,Ci,1,1] out as a linear weight [Co,Ci]."""
+
+    def __init__(self, src):
+        self.src = src
+
+    def has(self, k):
+        return self.src.has(k)
+
+    def get(self, k):
+        t = self.src.get(k)
+        return t.reshape(t.shape[0], -1) if t.ndim == 4 else t
+
+    def get_lora(self, m):
+        lo = self.src.get_lora(m)
+        if lo is None:
+            return None
+        a, b, s = lo
+        return a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1), s
+
+
+class Downsample2D:
+    def __init__(self, rt, src, p):
+        self.conv = Conv3x3(rt, src, p + ".conv", stride=2)
+
+    def __call__(self, x: FMap) -> FMap:
+        return self.conv(x, out_dtype=torch.float32)
+
+
+class Upsample2D:
+    def __init__(self, rt, src, p):
+        self.conv = Conv3x3(rt, src, p + ".conv")
+
+    def __call__(self, x: FMap) -> FMap:
+        return self.conv(x, out_dtype=torch.float32, up2=True)

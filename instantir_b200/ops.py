@@ -122,17 +122,11 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
     return out
 
 
-_gn_scratch = {}
-
-
 def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
+    # allocated per call (a few KiB from torch's caching allocator): a cached buffer would tie CUDA
+    # graphs captured at different times to one another's memory pools
     need = int(_lib.load().iir_groupnorm_scratch_floats(n_img, groups))
-    key = (device, torch.cuda.current_stream().cuda_stream)
-    buf = _gn_scratch.get(key)
-    if buf is None or buf.numel() < need:
-        buf = torch.empty(max(need, 1 << 16), dtype=torch.float32, device=device)
-        _gn_scratch[key] = buf
-    return buf
+    return torch.empty(need, dtype=torch.float32, device=device)
 
 
 def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int = 32,

@@ -1,0 +1,272 @@
+"""``InstantIRPipeline`` — the reference's denoising loop (pipelines/sdxl_instantir.py:1385-1666) on
+the sm_100a kernels, with the reference's call surface for this path: ``guidance_scale`` (--cfg),
+``preview_start``, ``control_guidance_end`` (--creative_start, infer.py:218-221),
+``previewer_scheduler``, ``num_inference_steps``, ``generator``, ``timesteps``,
+``controlnet_conditioning_scale``, ``init_latents_with_lq``, ``save_preview_row``...
+
+Scope: the per-timestep step.  The once-per-image encoders (CLIP text, DINOv2, VAE) are
+"next" rows, so this pipeline takes their OUTPUTS: ``prompt_embeds`` / ``pooled_prompt_embeds`` (and
+negatives), ``ip_adapter_image_embeds`` (DINOv2 tokens) and a 4-channel LQ latent as ``image`` (the
+reference accepts latents there too, :1370-1382) and returns latents (``output_type="latent"``).
+
+What changes versus the reference's loop (same results, fewer launches):
+  * which of the three step shapes runs at step i (previewer+aggregator+UNet / aggregator+UNet /
+    UNet only) is known on the host from controlnet_keep/previewing (:1415-1421) — no `.item()` sync;
+  * each model forward is captured once as a CUDA graph and replayed; timestep enters through a
+    device scalar;
+  * cond_scale multiplication, residual injection and torch.cat are one kernel inside the UNet;
+  * CFG combine + DDPM update are one kernel; the LCM preview step is one kernel;
+  * CFG-parallel (2 ranks: uncond / cond branch, one all-gather of eps per step) and data-parallel
+    sharding are provided by instantir_b200.parallel.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .schedulers import _randn
+
+
+def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None):
+    """pipelines/sdxl_instantir.py:195-237."""
+    if timesteps is not None:
+        scheduler.set_timesteps(timesteps=timesteps, device=device)
+        return scheduler.timesteps, len(scheduler.timesteps)
+    scheduler.set_timesteps(num_inference_steps, device=device)
+    return scheduler.timesteps, num_inference_steps
+
+
+def step_masks(n_steps, preview_start, preview_end, control_guidance_start, control_guidance_end):
+    """controlnet_keep / previewing (pipelines/sdxl_instantir.py:1415-1421)."""
+    keep, prev = [], []
+    for i in range(n_steps):
+        keep.append(1.0 - float(i / n_steps < control_guidance_start or (i + 1) / n_steps > control_guidance_end))
+        prev.append(1.0 - float(i / n_steps < preview_start or (i + 1) / n_steps > preview_end))
+    return keep, prev
+
+
+class _Graphed:
+    """fn() captured once as a CUDA graph over static tensors, replayed afterwards."""
+
+    def __init__(self, fn, enabled: bool):
+        self.fn, self.enabled, self.graph, self.out = fn, enabled, None, None
+
+    def __call__(self):
+        if not self.enabled:
+            return self.fn()
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy init, context caches)
+                self.fn()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = self.fn()
+            self.graph = g
+        self.graph.replay()
+        return self.out
+
+
+class InstantIRPipeline:
+    def __init__(self, unet, aggregator, scheduler, vae=None, text_encoder=None, text_encoder_2=None, tokenizer=None,
+                 tokenizer_2=None, feature_extractor=None, image_encoder=None):
+        self.unet, self.aggregator, self.scheduler = unet, aggregator, scheduler
+        self.vae, self.text_encoder, self.image_encoder = vae, text_encoder, image_encoder
+        self.device = unet.rt.device
+        self._graphs = {}
+
+    def prepare_previewers(self, previewer_lora_path=None, use_lcm=False):
+        """Reference: loads previewer_lora_weights.bin into a peft adapter then disables it (:350-397).
+        Here the LoRA is part of the UNet's weight source (merged into a second weight set at pack
+        time); this only validates that it is present and leaves the adapter disabled."""
+        if not any(a.to_out[0].w.lora is not None for _, a in self.unet.attention_modules()):
+            raise ValueError("the UNet was built from a weight source without previewer LoRA tensors")
+        self.unet.disable_adapters()
+        return None
+
+    # ------------------------------------------------------------------------------------ checks
+    def check_inputs(self, image, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
+                     negative_pooled_prompt_embeds, ip_adapter_image_embeds, guidance_scale,
+                     control_guidance_start, control_guidance_end, previewer_scheduler, preview_start):
+        if prompt_embeds is None:
+            raise ValueError("Provide `prompt_embeds` (the CLIP text encoders are outside this build's scope, SURVEY §8 f2).")
+        if pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if guidance_scale > 1.0 and (negative_prompt_embeds is None or negative_pooled_prompt_embeds is None):
+            raise ValueError("classifier-free guidance needs `negative_prompt_embeds` and `negative_pooled_prompt_embeds`.")
+        if negative_prompt_embeds is not None and prompt_embeds.shape != negative_prompt_embeds.shape:
+            raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed directly, "
+                             f"but got {prompt_embeds.shape} != {negative_prompt_embeds.shape}.")
+        if not torch.is_tensor(image) or image.ndim != 4 or image.shape[1] != self.unet.cfg.in_channels:
+            raise TypeError("`image` must be a 4-channel latent tensor [B,4,h,w] (VAE encode is outside this build's scope)")
+        if ip_adapter_image_embeds is None:
+            raise ValueError("Provide `ip_adapter_image_embeds` (DINOv2 tokens [2,B,S,D] or a list holding that tensor).")
+        if control_guidance_start >= control_guidance_end:
+            raise ValueError(f"control guidance start: {control_guidance_start} cannot be larger or equal to control guidance end: {control_guidance_end}.")
+        if control_guidance_start < 0.0:
+            raise ValueError(f"control guidance start: {control_guidance_start} can't be smaller than 0.")
+        if control_guidance_end > 1.0:
+            raise ValueError(f"control guidance end: {control_guidance_end} can't be larger than 1.0.")
+        if preview_start < 1.0 and previewer_scheduler is None:
+            raise ValueError("previewing steps need `previewer_scheduler` (LCMSingleStepScheduler)")
+
+    # -------------------------------------------------------------------------------------- call
+    @torch.no_grad()
+    def __call__(self, prompt=None, prompt_2=None, image=None, height=None, width=None, num_inference_steps=30,
+                 timesteps: Optional[List[int]] = None, denoising_end=None, guidance_scale=7.0, negative_prompt=None,
+                 negative_prompt_2=None, num_images_per_prompt=1, eta=0.0, generator=None, latents=None,
+                 prompt_embeds=None, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+                 negative_pooled_prompt_embeds=None, ip_adapter_image=None, ip_adapter_image_embeds=None,
+                 output_type="latent", return_dict=True, cross_attention_kwargs=None, guidance_rescale=0.0,
+                 original_size=None, crops_coords_top_left=(0, 0), target_size=None, save_preview_row=False,
+                 init_latents_with_lq=True, multistep_restore=False, adastep_restore=False, previewer_scheduler=None,
+                 preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
+                 controlnet_conditioning_scale=1.0, reference_latents=None, use_cuda_graph=True, cfg_parallel=None,
+                 dp_shard=None, record=None, **kwargs):
+        if prompt is not None or negative_prompt is not None or ip_adapter_image is not None:
+            raise NotImplementedError("text / image encoders are outside this build's scope (SURVEY §8 f1-f2): pass "
+                                      "prompt_embeds, pooled_prompt_embeds, ip_adapter_image_embeds and a latent `image`")
+        if multistep_restore or adastep_restore or guidance_rescale or denoising_end or reference_latents is not None:
+            raise NotImplementedError("multistep_restore / adastep_restore / guidance_rescale / denoising_end / "
+                                      "reference_latents are experimental reference options (SURVEY §8 f4)")
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is outside this build's scope (SURVEY §8 f1): use output_type='latent'")
+        self.check_inputs(image, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
+                          negative_pooled_prompt_embeds, ip_adapter_image_embeds, guidance_scale,
+                          control_guidance_start, control_guidance_end, previewer_scheduler, preview_start)
+        dev = self.device
+        unet, agg, sched = self.unet, self.aggregator, self.scheduler
+        # dp_shard=(total_images, slice): this rank restores images[slice] of a data-parallel job; noise is
+        # drawn for the FULL batch and sliced so the sharded run is bit-comparable with the unsharded one
+        if dp_shard is not None:
+            total_b, sl = dp_shard
+
+            def draw(shape):
+                return _randn((total_b,) + tuple(shape[1:]), generator, dev)[sl].contiguous()
+        else:
+            def draw(shape):
+                return _randn(tuple(shape), generator, dev)
+        do_cfg = guidance_scale > 1.0
+        f32 = dict(device=dev, dtype=torch.float32)
+        image = image.to(**f32).contiguous()
+        B, _, h, w = image.shape
+        H_px, W_px = height or h * 8, width or w * 8
+        ts, num_inference_steps = retrieve_timesteps(sched, num_inference_steps, dev, timesteps)
+        n = len(ts)
+        # 6. latents: LQ latent noised to t0 with the user's generator (:931-939, :1388-1389)
+        if latents is not None:
+            latents = latents.to(**f32).contiguous()
+        elif init_latents_with_lq:
+            latents = sched.add_noise(image, draw(image.shape), ts[:1])
+        else:
+            latents = draw(image.shape) * sched.init_noise_sigma
+        keep, previewing = step_masks(n, preview_start, preview_end, control_guidance_start, control_guidance_end)
+        scales = controlnet_conditioning_scale if isinstance(controlnet_conditioning_scale, list) else [controlnet_conditioning_scale] * n
+        if len(scales) != n:
+            raise ValueError(f"{len(scales)} controlnet scales do not match number of sampling steps {n}")
+        # 7.2 added time ids (:1428-1455)
+        original_size = original_size or (H_px, W_px)
+        target_size = target_size or (H_px, W_px)
+        time_ids = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)], **f32).repeat(B, 1)
+        if isinstance(ip_adapter_image_embeds, list):
+            ip_adapter_image_embeds = ip_adapter_image_embeds[0]
+        ip = ip_adapter_image_embeds.to(**f32)
+        if ip.ndim != 4 or ip.shape[0] != 2:
+            raise ValueError("ip_adapter_image_embeds must be [2, B, S, D] (negative, positive) DINOv2 tokens")
+        # branch layout: CFG batch = [uncond; cond] (:1457-1460); a CFG-parallel rank keeps one branch
+        branches = [0, 1] if do_cfg else [1]
+        if cfg_parallel is not None:
+            if not do_cfg:
+                raise ValueError("cfg_parallel needs guidance_scale > 1")
+            branches = [cfg_parallel.branch]
+        pe = {0: negative_prompt_embeds, 1: prompt_embeds}
+        pp = {0: negative_pooled_prompt_embeds, 1: pooled_prompt_embeds}
+        prompt_all = torch.cat([pe[b].to(**f32) for b in branches], 0).contiguous()
+        pooled_all = torch.cat([pp[b].to(**f32) for b in branches], 0).contiguous()
+        time_ids_all = time_ids.repeat(len(branches), 1).contiguous()
+        image_all = torch.cat([image] * len(branches), 0).contiguous()
+        ip_all = [torch.cat([ip[b] for b in branches], 0).unsqueeze(1).contiguous()]
+        nb = len(branches) * B
+        added = {"text_embeds": pooled_all, "time_ids": time_ids_all, "image_embeds": ip_all}
+        agg_added = {"text_embeds": pooled_all, "time_ids": time_ids_all}
+
+        # static tensors the captured graphs read / write
+        x_in = torch.empty(nb, 4, h, w, **f32)
+        t_dev = torch.empty(1, **f32)
+        cond_scale = torch.empty(nb, **f32)
+        preview_latent = torch.empty(nb, 4, h, w, **f32)
+        st = SimpleNamespace(down=None, mid=None)
+        unet.refresh_context(prompt_all, added, None)
+
+        def f_preview():
+            unet.enable_adapters()
+            try:
+                return unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added, return_dict=False)[0]
+            finally:
+                unet.disable_adapters()
+
+        def f_agg(cond):
+            return lambda: agg(image_all, t_dev, encoder_hidden_states=prompt_all, controlnet_cond=cond,
+                               added_cond_kwargs=agg_added, return_dict=False)
+
+        def f_unet(with_res):
+            def run():
+                if with_res:
+                    return unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added,
+                                down_block_additional_residuals=st.down, mid_block_additional_residual=st.mid,
+                                additional_residual_scale=cond_scale, return_dict=False)[0]
+                return unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added, return_dict=False)[0]
+            return run
+
+        g_preview = _Graphed(f_preview, use_cuda_graph)
+        g_agg_prev = _Graphed(f_agg(preview_latent), use_cuda_graph)
+        g_agg_lq = _Graphed(f_agg(image_all), use_cuda_graph)
+        # one graph per residual source: the captured UNet reads the static outputs of that aggregator graph
+        g_unet_res = {"prev": _Graphed(f_unet(True), use_cuda_graph), "lq": _Graphed(f_unet(True), use_cuda_graph)}
+        res_src = None
+        g_unet_plain = _Graphed(f_unet(False), use_cuda_graph)
+
+        preview_row = []
+        for i, t in enumerate(ts):
+            t_int = int(t)
+            t_dev.fill_(float(t_int))
+            for k in range(len(branches)):
+                x_in[k * B:(k + 1) * B].copy_(latents)  # torch.cat([latents]*2) (:1503); scale_model_input = id
+            cs = min(max(1.0, 0.0), float(scales[i])) * keep[i]  # preview_factor == 1 without adastep_restore
+            cond_scale.fill_(cs)
+            if cs > 0.1:  # the `(cond_scale>0.1).sum().item() > 0` gate (:1542), decided on the host
+                if previewing[i] > 0:
+                    preview_noise = g_preview()
+                    previewer_scheduler.step(preview_noise, t_int, x_in, return_dict=False, out=preview_latent)
+                    if save_preview_row:
+                        preview_row.append(preview_latent[-B:].clone())
+                    st.down, st.mid = g_agg_prev()
+                    res_src = "prev"
+                else:
+                    st.down, st.mid = g_agg_lq()
+                    res_src = "lq"
+            if st.down is None:
+                if cs > 0:
+                    raise RuntimeError("control is active but no aggregator features exist")
+                noise_pred = g_unet_plain()  # reference would raise NameError here; UNet-only is the intent
+            elif cs == 0.0:
+                noise_pred = g_unet_plain()  # stale residuals x 0 (:1602-1603) == no residuals
+            else:
+                noise_pred = g_unet_res[res_src]()
+            if cfg_parallel is not None:
+                noise_pred = cfg_parallel.gather_branches(noise_pred)  # [2B,4,h,w] = [uncond; cond]
+            out = sched.step(noise_pred, t_int, latents, generator=generator, return_dict=True,
+                             guidance=guidance_scale if do_cfg else None,
+                             noise=draw(latents.shape) if t_int > 0 else None)
+            latents = out.prev_sample
+            if record is not None:
+                record.setdefault("latents", []).append(latents.clone())
+                record.setdefault("pred_x0", []).append(out.pred_original_sample.clone())
+                record.setdefault("preview", []).append(preview_latent.clone() if (cs > 0.1 and previewing[i] > 0) else None)
+        if not return_dict:
+            return (latents, preview_row) if save_preview_row else (latents,)
+        return SimpleNamespace(images=latents, preview_rows=preview_row if save_preview_row else None)

@@ -1,0 +1,143 @@
+"""Model-level parity on the GPU, through the reference-shaped Python API which calls the C ABI.
+
+Tolerances are the north star's: relative L2 <= 1e-4 in the fp32 check mode, <= 1e-2 in bf16 for
+per-step latents (module outputs in bf16 get 2e-2: they are not yet damped by the scheduler step).
+Golden comparisons use vectors produced by running the reference's own files (tests/golden)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _util import build_oracle, export_state, make_inputs, rel_l2  # noqa: E402
+from seeding import seeded_init  # noqa: E402
+
+from instantir_b200 import config as pcfg  # noqa: E402
+from instantir_b200 import weights  # noqa: E402
+from instantir_b200.aggregator import Aggregator  # noqa: E402
+from instantir_b200.nn import Runtime  # noqa: E402
+from instantir_b200.pipeline import InstantIRPipeline  # noqa: E402
+from instantir_b200.resampler import Resampler  # noqa: E402
+from instantir_b200.schedulers import DDPMScheduler, LCMSingleStepScheduler  # noqa: E402
+from instantir_b200.unet import UNet2DConditionModel  # noqa: E402
+from oracle import config as ocfg  # noqa: E402
+from oracle import model as om  # noqa: E402
+from oracle import pipeline as opipe  # noqa: E402
+from oracle import schedulers as osched  # noqa: E402
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda"
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+torch.set_grad_enabled(False)
+
+
+def _pcfg_from(oc):
+    return pcfg.ModelConfig(**oc.to_dict())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_base_mode_vs_reference_min_sdxl_vector(precision):
+    """product UNet (no adapter: text-only cross-attention) vs the output of the reference's
+    module/min_sdxl.py forward (tests/golden/min_sdxl.pt)."""
+    g = torch.load(os.path.join(G, "min_sdxl.pt"))
+    oc = ocfg.StepConfig(block_out_channels=(64, 128, 256), transformer_layers_per_block=(1, 1, 2),
+                         num_attention_heads=(1, 2, 4), cross_attention_dim=2048, addition_time_embed_dim=32,
+                         pooled_dim=64, time_embed_dim=1280)
+    ounet = seeded_init(om.UNet2DConditionModel(oc), g["seeds"]["unet"])
+    sd, _ = export_state(ounet)
+    unet = UNet2DConditionModel(_pcfg_from(oc), weights.StateDictSource(sd, DEV), DEV, precision, adapter=False)
+    out = unet(g["sample"].to(DEV), torch.tensor(g["t"]), g["text"].to(DEV),
+               added_cond_kwargs={"text_embeds": g["pooled"].to(DEV), "time_ids": g["time_ids"].to(DEV)})[0]
+    torch.cuda.synchronize()
+    assert rel_l2(out, g["unet_out"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_aggregator_vs_reference_forward_vector(precision):
+    """product Aggregator vs the output of the reference's module/aggregator.py forward."""
+    g = torch.load(os.path.join(G, "aggregator.pt"))
+    oc = ocfg.StepConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    oagg = om.Aggregator(oc)
+    om.remove_attn2(oagg)
+    seeded_init(oagg, g["seed"])
+    sd, _ = export_state(oagg)
+    agg = Aggregator(_pcfg_from(oc), weights.StateDictSource(sd, DEV), DEV, precision)
+    i = g["inputs"]
+    down, mid = agg(i["sample"].to(DEV), torch.tensor(i["t"]), None, controlnet_cond=i["cond"].to(DEV),
+                    added_cond_kwargs={"text_embeds": i["pooled"].to(DEV), "time_ids": i["time_ids"].to(DEV)})
+    torch.cuda.synchronize()
+    assert len(down) == 9
+    for a, b in zip(down, g["down"]):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert rel_l2(a, b) < TOL[precision]
+    assert rel_l2(mid, g["mid"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_resampler_vs_reference_vector(precision):
+    g = torch.load(os.path.join(G, "resampler.pt"))
+    ors = seeded_init(om.Resampler(dim=128, depth=2, dim_head=64, heads=2, num_queries=16, embedding_dim=64,
+                                   output_dim=256, ff_mult=4), g["seed"])
+    cfg = pcfg.tiny()
+    sd = {"rs." + k: v for k, v in ors.state_dict().items()}
+    rs = Resampler(Runtime(DEV, precision), weights.StateDictSource(sd, DEV), "rs", cfg)
+    x = g["x"].to(DEV)
+    out = rs(x.reshape(x.shape[0] * x.shape[1], *x.shape[2:]))
+    torch.cuda.synchronize()
+    assert rel_l2(out, g["out"]) < (1e-4 if precision == "fp32" else 1e-2)
+
+
+def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0, cge=1.0, graph=True, guidance=7.0):
+    oc = getattr(ocfg, cfg_name)()
+    alpha = 8.0
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=alpha)
+    inp = make_inputs(oc, B=B, h=h, w=h)
+    rec_o = {}
+    ref = opipe.restore_latents(
+        ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], num_inference_steps=steps, guidance_scale=guidance,
+        preview_start=preview_start, control_guidance_end=cge, generator=torch.Generator().manual_seed(42), record=rec_o)
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = _pcfg_from(oc)
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=alpha / oc.lora_rank), DEV, precision)
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, precision)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+    pipe.prepare_previewers()
+    rec_p = {}
+    out = pipe(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+               pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+               ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=steps, guidance_scale=guidance,
+               previewer_scheduler=LCMSingleStepScheduler(), preview_start=preview_start, control_guidance_end=cge,
+               generator=torch.Generator().manual_seed(42), use_cuda_graph=graph, record=rec_p)
+    torch.cuda.synchronize()
+    return ref, rec_o, out.images, rec_p
+
+
+@pytest.mark.parametrize("precision,graph", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_full_step_config1_vs_oracle(precision, graph):
+    """BASELINE config 1: scaled-down UNet + aggregator + IP-adapter + LoRA previewer, 256², 2 steps,
+    CFG 7 — per-step latent relative L2 vs the oracle (1e-4 fp32 / 1e-2 bf16)."""
+    ref, rec_o, out, rec_p = _run_pair(precision, graph=graph)
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+        assert rel_l2(a, b) < tol, f"step {i}"
+    for a, b in zip(rec_p["preview"], rec_o["preview"]):
+        if b is not None:
+            assert rel_l2(a, b) < (1e-4 if precision == "fp32" else 3e-2)
+    assert rel_l2(out, ref) < tol
+
+
+def test_step_shapes_no_preview_and_unet_only_fp32():
+    """preview_start=1 (aggregator fed the LQ latent) and control_guidance_end=0.5 (second step UNet-only)."""
+    ref, rec_o, out, rec_p = _run_pair("fp32", preview_start=1.0, cge=0.5, graph=True)
+    for a, b in zip(rec_p["latents"], rec_o["latents"]):
+        assert rel_l2(a, b) < 1e-4
+
+
+def test_guidance_scale_le_1_disables_cfg_fp32():
+    ref, _, out, _ = _run_pair("fp32", steps=1, guidance=1.0, graph=False)
+    assert rel_l2(out, ref) < 1e-4

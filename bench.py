@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — InstantIR denoising-step benchmark (driver contract, hot-path tier).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg-parallel]
+                    [--workload config2|config3|config1] [--batch B]
+
+A "step" is one denoising step of the hot path over one batch of synthetic input:
+Aggregator forward + UNet forward (both CFG branches) + fused CFG/DDPM update (+ previewer UNet
+forward and LCM step for config3).  Default workload = BASELINE.json configs[1]: full SDXL UNet +
+InstantIR aggregator, random-init weights, 1024² (latent 128²), 30-step schedule, CFG 7, previewer off.
+
+metric  = 1024² restored images / s (one image = 30 steps), whole job over all ranks
+value   = device-timed, inputs resident in HBM (CUDA events, max over ranks)
+e2e     = the same metric through the public API (InstantIRPipeline.__call__) from pinned HOST
+          buffers: H2D of the image's conditioning, context refresh, 30 steps, D2H of the result
+roofline= the dominant kernel class (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs of its
+          launches in one step / their CUDA-event time, vs MEASURED_PEAKS.json
+cpu_baseline = the CPU oracle (port of the reference path) on this box's host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STEPS_PER_IMAGE = 30
+# algorithmic FLOPs per image-step at 1024², both CFG branches (SURVEY.md §8d / BASELINE.md §2)
+FLOPS_STEP = {"config2": 25.89e12, "config3": 39.36e12}
+FLOPS_UNET_BRANCH = {128: 6.737e12, 64: None, 32: 0.378e12}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+class CpuReferenceSample:
+    """The CPU oracle (port of the reference's PyTorch path, fp32) on a bounded sample of the
+    config-2 workload: ONE UNet forward of ONE CFG branch at full SDXL widths (IP-adapter processors
+    + Resampler installed), latent `latent`x`latent`."""
+
+    def __init__(self, latent, threads=None):
+        import torch
+
+        from oracle import config as ocfg
+        from oracle import model as om
+
+        self.torch = torch
+        self.latent = latent
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        torch.set_grad_enabled(False)
+        cfg = ocfg.sdxl()
+        self.unet = unet = om.load_adapter(om.UNet2DConditionModel(cfg))
+        g = torch.Generator().manual_seed(0)
+        for name, p in unet.named_parameters():  # cheap, numerically sane init (timing only)
+            if p.ndim >= 2:
+                p.uniform_(-1.0, 1.0, generator=g).mul_((3.0 / p[0].numel()) ** 0.5)
+            else:
+                p.fill_(1.0 if ("norm" in name and name.endswith("weight")) else 0.0)
+        self.x = torch.randn(1, 4, latent, latent, generator=g)
+        self.text = torch.randn(1, 77, 2048, generator=g)
+        self.added = {"text_embeds": torch.randn(1, 1280, generator=g),
+                      "time_ids": torch.tensor([[latent * 8.0, latent * 8.0, 0.0, 0.0, latent * 8.0, latent * 8.0]]),
+                      "image_embeds": [torch.randn(1, 1, 257, 1024, generator=g)]}
+        # FLOPs of the sample "as executed" (incl. step-invariant K/V + Resampler)
+        self.flops = {128: 6.833e12 + 0.018e12, 64: 1.639e12 + 0.018e12, 32: 0.474e12 + 0.018e12}[latent]
+
+    def run(self):
+        torch, unet = self.torch, self.unet
+        t = torch.tensor(501)
+        t0 = time.perf_counter()
+        emb = unet.time_embedding(unet.get_time_embed(self.x, t))
+        emb = emb + unet.get_aug_embed(emb, self.text, self.added)
+        out = unet(self.x, t, self.text, cross_attention_kwargs={"temb": emb}, added_cond_kwargs=self.added)[0]
+        dt = time.perf_counter() - t0
+        assert bool(torch.isfinite(out).all())
+        return dt
+
+
+def _cpu_latent():
+    cores = os.cpu_count() or 1
+    return 128 if cores >= 48 else 64 if cores >= 12 else 32
+
+
+def cpu_baseline(latent=None):
+    smp = CpuReferenceSample(latent or _cpu_latent())
+    smp.run()  # warm-up (thread pools, allocator)
+    dt = smp.run()
+    # one image-step of config 2 executes 26.12 TFLOP on the reference path (SURVEY §8d "as executed")
+    step_s = dt * (26.12e12 / smp.flops)
+    img_s = 1.0 / (STEPS_PER_IMAGE * step_s)
+    return {"value": img_s, "unit": "img/s", "cores": smp.threads, "kind": "port",
+            "sample": f"oracle UNet forward, 1 CFG branch, full SDXL widths + IP-adapter, latent {smp.latent}x{smp.latent}: "
+                      f"{dt:.2f} s for {smp.flops / 1e12:.2f} TFLOP fp32 ({smp.flops / dt / 1e12:.3f} TFLOP/s); scaled by executed "
+                      f"FLOPs to a 30-step 1024² image (26.12 TFLOP/step)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (the oracle port; diffusers is absent so the reference
+    itself cannot run) on this box's host cores; each step = the bounded sample above."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    smp = CpuReferenceSample(_cpu_latent())
+    latent, flops, threads = smp.latent, smp.flops, smp.threads
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        dt = smp.run()
+        if i >= args.warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > 150 and times:  # keep the whole run within a few minutes
+            break
+    dt = statistics.mean(times)
+    step_s = dt * (26.12e12 / flops)
+    img_s = 1.0 / (STEPS_PER_IMAGE * step_s)
+    line = {"impl": "reference", "metric": "1024x1024 restored images per second (30 steps, CFG 7)", "value": img_s,
+            "unit": "img/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: full SDXL UNet + InstantIR aggregator, random-init, 1024², 30 steps, CFG 7, "
+                                   "previewer off — CPU oracle port, bounded sample scaled by FLOPs"},
+            "cpu_baseline": {"value": img_s, "unit": "img/s", "cores": threads, "kind": "port",
+                             "sample": f"UNet forward, 1 CFG branch, latent {latent}: {dt:.2f} s mean of {len(times)}"},
+            "e2e": {"value": img_s, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def build_models(cfg, dev, precision, with_lora):
+    from instantir_b200 import weights
+    from instantir_b200.aggregator import Aggregator
+    from instantir_b200.unet import UNet2DConditionModel
+
+    ushapes = weights.unet_param_shapes(cfg, adapter=True)
+    lshapes = weights.lora_param_shapes(cfg, ushapes) if with_lora else None
+    unet = UNet2DConditionModel(cfg, weights.RandomSource(ushapes, dev, seed=0, lora_shapes=lshapes, lora_scale=1.0), dev, precision)
+    agg = Aggregator(cfg, weights.RandomSource(weights.aggregator_param_shapes(cfg), dev, seed=1), dev, precision)
+    return unet, agg
+
+
+def host_inputs(cfg, B, latent, seed=1234):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+
+    def r(*s):
+        return torch.randn(*s, generator=g).pin_memory()
+
+    base_p, base_q = torch.randn(B, cfg.text_seq_len, cfg.cross_attention_dim, generator=g), torch.randn(B, cfg.pooled_dim, generator=g)
+    return dict(
+        image=(r(B, 4, latent, latent) * 0.8).pin_memory(),
+        prompt_embeds=(base_p + 0.15 * r(B, cfg.text_seq_len, cfg.cross_attention_dim)).pin_memory(),
+        negative_prompt_embeds=(base_p + 0.15 * r(B, cfg.text_seq_len, cfg.cross_attention_dim)).pin_memory(),
+        pooled_prompt_embeds=(base_q + 0.15 * r(B, cfg.pooled_dim)).pin_memory(),
+        negative_pooled_prompt_embeds=(base_q + 0.15 * r(B, cfg.pooled_dim)).pin_memory(),
+        ip_adapter_image_embeds=torch.stack([0.3 * r(B, cfg.image_seq_len, cfg.image_embed_dim),
+                                             r(B, cfg.image_seq_len, cfg.image_embed_dim)]).pin_memory())
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from instantir_b200 import config as pcfg
+    from instantir_b200 import ops, parallel
+    from instantir_b200.pipeline import InstantIRPipeline, LaunchCounter
+    from instantir_b200.schedulers import DDPMScheduler, LCMSingleStepScheduler
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    torch.set_grad_enabled(False)
+
+    wl = args.workload
+    cfg = pcfg.tiny() if wl == "config1" else pcfg.sdxl()
+    latent = 32 if wl == "config1" else 128
+    preview = wl == "config3"
+    B = args.batch
+    unet, agg = build_models(cfg, dev, "bf16", with_lora=preview)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+    cfgp = parallel.CFGParallel() if (args.cfg_parallel and world > 1) else None
+    host = host_inputs(cfg, B, latent, seed=1234 + (rank // 2 if cfgp else rank))
+    call_kw = dict(num_inference_steps=STEPS_PER_IMAGE, guidance_scale=7.0, previewer_scheduler=LCMSingleStepScheduler(),
+                   preview_start=0.0 if preview else 1.0, cfg_parallel=cfgp, use_cuda_graph=True)
+
+    # ---- device-resident leg: inputs already in HBM, K steps timed with CUDA events
+    devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    gen = torch.Generator(device=dev).manual_seed(42)
+    loop = pipe(**devin, generator=gen, prepare_only=True, **call_kw)
+    n_sched = loop.n_steps
+    for i in range(args.warmup):
+        loop.step(i % n_sched)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = LaunchCounter.total()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loop.step((args.warmup + i) % n_sched)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = LaunchCounter.total() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    assert bool(torch.isfinite(loop.latents).all()), "non-finite latents"
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    ms_per_step = ms / args.steps
+    n_images = B * (world // 2 if cfgp else world)
+    value = n_images / (STEPS_PER_IMAGE * ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: public API from pinned host buffers, one image = 30 steps
+    def e2e_once():
+        out = pipe(**{k: v.to(dev, non_blocking=True) for k, v in host.items()}, generator=gen, **call_kw).images
+        return out.to("cpu", non_blocking=False)
+
+    e2e_once()  # warm (captures this call's graphs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = max(1, min(3, args.steps // 10))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = e2e_once()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / reps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = res.numel() * res.element_size()
+
+    if rank == 0:
+        # ---- roofline leg: one eager step with CUDA events around every launch
+        pk, pk_src = peaks()
+        ops.PROFILE = []
+        loop2 = pipe(**devin, generator=gen, prepare_only=True, **dict(call_kw, use_cuda_graph=False, cfg_parallel=None)) \
+            if cfgp is None else None
+        roof = None
+        breakdown = {}
+        if loop2 is not None:
+            loop2.step(0)
+            ops.PROFILE = []
+            loop2.step(1)
+            torch.cuda.synchronize()
+            for name, work, a, b in ops.PROFILE:
+                d = breakdown.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+                d["launches"] += 1
+                d["ms"] += a.elapsed_time(b)
+                d["flops"] += work.get("flops", 0.0)
+                d["bytes"] += work.get("bytes", 0.0)
+            ops.PROFILE = None
+            tc = {"launches": 0, "ms": 0.0, "flops": 0.0}
+            for k in ("gemm_tc", "conv3x3_tc"):
+                if k in breakdown:
+                    for f in tc:
+                        tc[f] += breakdown[k][f]
+            if tc["launches"]:
+                ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
+                peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+                roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                        "launches_per_step": tc["launches"], "ms_per_step": tc["ms"],
+                        "flops_per_launch_avg": tc["flops"] / tc["launches"]}
+            for d in breakdown.values():
+                d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] and d["flops"] else None
+                d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] and d["bytes"] else None
+        step_flops = FLOPS_STEP.get(wl)
+        line = {
+            "metric": "1024x1024 restored images per second (30 steps, CFG 7)" if wl != "config1" else "256x256 restored images per second (30-step schedule, CFG 7)",
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": {"config2": "BASELINE configs[1]: full SDXL UNet + InstantIR aggregator + IP-adapter, random-init, 1024² (latent 128²), 30-step DDPM schedule, CFG 7, previewer off",
+                                    "config3": "BASELINE configs[2]: config 2 + LCM previewer every step (preview_start=0)",
+                                    "config1": "BASELINE configs[0]: scaled-down step, 256²"}[wl],
+                       "images_per_rank": B, "parallelism": ("cfg-parallel pairs x dp" if cfgp else f"dp{world}"),
+                       "step": "aggregator fwd + UNet fwd (2 CFG branches) + fused CFG/DDPM" + (" + previewer UNet fwd + LCM" if preview else ""),
+                       "l2": "inputs larger than L2: ~8.6 GB of bf16 weights are streamed every step (L2 = 126 MB)",
+                       "cuda_graphs": True},
+            "clocks": clocks,
+            "e2e": {"value": n_images / e2e_s, "unit": "img/s", "h2d_bytes_per_step": h2d / STEPS_PER_IMAGE,
+                    "d2h_bytes_per_step": d2h / STEPS_PER_IMAGE, "seconds_per_image_batch": e2e_s,
+                    "note": "copies happen once per image (30 steps); bytes are per denoising step"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_tflops": (step_flops * B / (ms_per_step * 1e-3) / 1e12) if step_flops else None,
+            "step_frac_of_sustained_peak": (step_flops * B / (ms_per_step * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)) if step_flops else None,
+            "kernel_breakdown": breakdown,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3"])
+    ap.add_argument("--batch", type=int, default=1, help="images per rank")
+    ap.add_argument("--cfg-parallel", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

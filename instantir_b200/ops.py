@@ -15,6 +15,30 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, BF16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
 
 
+# ---- optional per-launch profiling (bench.py's roofline leg): when PROFILE is a list every op
+# appends (kernel name, work dict, start event, end event); events are recorded on the launching
+# stream around the C-ABI call.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, name, **work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.append((self.name, self.work, self.e0, self.e1))
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return F32
@@ -83,7 +107,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.act, g.pair = act, pair
     g.bn = bn if bn is not None else default_bn(N, bool(pair))
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
-    _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt")
+    name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
+    with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K):
+        _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt")
     return out
 
 
@@ -92,10 +118,11 @@ def conv3x3_direct(x, w, bias, out, *, in_nchw: bool, out_nchw: bool, n_img: int
     lib = _lib.load()
     _f32c(w, "w")
     _f32c(bias, "bias")
-    _lib.check(lib.iir_conv3x3_direct(_p(x), _dt(x), int(in_nchw), _p(w), _p(bias), _p(out), _dt(out),
-                                      int(out_nchw), n_img, H, W, Cin, Cout,
-                                      out_H if out_H is not None else H, out_row_off, _stream()),
-               "iir_conv3x3_direct")
+    with _Prof("conv3x3_direct", bytes=float(n_img) * H * W * (Cin * x.element_size() + Cout * out.element_size())):
+        _lib.check(lib.iir_conv3x3_direct(_p(x), _dt(x), int(in_nchw), _p(w), _p(bias), _p(out), _dt(out),
+                                          int(out_nchw), n_img, H, W, Cin, Cout,
+                                          out_H if out_H is not None else H, out_row_off, _stream()),
+                   "iir_conv3x3_direct")
     return out
 
 
@@ -118,7 +145,8 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
     a.B, a.heads, a.n_q = B, heads, n_q
     a.softmax_scale = softmax_scale
     fn = lib.iir_attn_tc if tc else lib.iir_attn_simt
-    _lib.check(fn(C.byref(a), _stream()), "iir_attn_tc" if tc else "iir_attn_simt")
+    with _Prof("attn_tc" if tc else "attn_simt", flops=4.0 * B * heads * n_q * sum(kv_lens) * 64, n_q=n_q, n_kv=sum(kv_lens)):
+        _lib.check(fn(C.byref(a), _stream()), "iir_attn_tc" if tc else "iir_attn_simt")
     return out
 
 
@@ -133,50 +161,56 @@ def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int =
               eps: float = 1e-5, silu: bool = False):
     lib = _lib.load()
     part = _gn_partials(x.device, n_img, groups)
-    _lib.check(lib.iir_groupnorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
-                                 _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _p(part),
-                                 _stream()), "iir_groupnorm")
+    with _Prof("groupnorm", bytes=float(n_img) * HW * C * (2 * x.element_size() + out.element_size())):
+        _lib.check(lib.iir_groupnorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
+                                     _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _p(part),
+                                     _stream()), "iir_groupnorm")
     return out
 
 
 def layernorm(x, gamma, beta, out, *, rows: int, C: int, eps: float = 1e-5, mod=None,
               rows_per_sample: int = 0):
     lib = _lib.load()
-    _lib.check(lib.iir_layernorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
-                                 _p(_f32c(mod, "mod")), rows_per_sample, _p(out), _dt(out), rows, C,
-                                 eps, _stream()), "iir_layernorm")
+    with _Prof("layernorm", bytes=float(rows) * C * (x.element_size() + out.element_size())):
+        _lib.check(lib.iir_layernorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
+                                     _p(_f32c(mod, "mod")), rows_per_sample, _p(out), _dt(out), rows, C,
+                                     eps, _stream()), "iir_layernorm")
     return out
 
 
 def concat_inject(h, C1: int, skip, C2: int, out, *, M: int, rh=None, rs=None, cond_scale=None,
                   rows_per_sample: int = 0):
     lib = _lib.load()
-    _lib.check(lib.iir_concat_inject(_p(h), _dt(h), C1, _p(rh), _dt(rh) if rh is not None else 0,
-                                     _p(skip), _dt(skip) if skip is not None else 0, C2, _p(rs),
-                                     _dt(rs) if rs is not None else 0, _p(_f32c(cond_scale, "cond_scale")),
-                                     rows_per_sample, _p(out), _dt(out), M, _stream()),
-               "iir_concat_inject")
+    with _Prof("concat_inject", bytes=float(M) * (C1 + C2) * (h.element_size() + out.element_size())):
+        _lib.check(lib.iir_concat_inject(_p(h), _dt(h), C1, _p(rh), _dt(rh) if rh is not None else 0,
+                                         _p(skip), _dt(skip) if skip is not None else 0, C2, _p(rs),
+                                         _dt(rs) if rs is not None else 0, _p(_f32c(cond_scale, "cond_scale")),
+                                         rows_per_sample, _p(out), _dt(out), M, _stream()),
+                   "iir_concat_inject")
     return out
 
 
 def upsample2x(x, out, *, n_img: int, H: int, W: int, C: int):
     lib = _lib.load()
-    _lib.check(lib.iir_upsample2x(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
-               "iir_upsample2x")
+    with _Prof("upsample2x", bytes=float(n_img) * H * W * C * (x.element_size() + 4 * out.element_size())):
+        _lib.check(lib.iir_upsample2x(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
+                   "iir_upsample2x")
     return out
 
 
 def im2col3x3_s2(x, out, *, n_img: int, H: int, W: int, C: int):
     lib = _lib.load()
-    _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
-               "iir_im2col3x3_s2")
+    with _Prof("im2col3x3_s2", bytes=float(n_img) * H * W * C * (x.element_size() + 2.25 * out.element_size())):
+        _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
+                   "iir_im2col3x3_s2")
     return out
 
 
 def cast2d(x, ld_in: int, out, ld_out: int, *, rows: int, cols: int):
     lib = _lib.load()
-    _lib.check(lib.iir_cast2d(_p(x), _dt(x), ld_in, _p(out), _dt(out), ld_out, rows, cols, _stream()),
-               "iir_cast2d")
+    with _Prof("cast2d", bytes=float(rows) * cols * (x.element_size() + out.element_size())):
+        _lib.check(lib.iir_cast2d(_p(x), _dt(x), ld_in, _p(out), _dt(out), ld_out, rows, cols, _stream()),
+                   "iir_cast2d")
     return out
 
 
@@ -203,8 +237,9 @@ def timestep_embedding(t, dim: int, out):
 
 def linear_small(x, w, bias, out, *, M: int, N: int, K: int, act: int = ACT_NONE):
     lib = _lib.load()
-    _lib.check(lib.iir_linear_small(_p(x), _dt(x), _p(w), _dt(w), _p(_f32c(bias, "bias")), _p(out),
-                                    _dt(out), M, N, K, act, _stream()), "iir_linear_small")
+    with _Prof("linear_small", bytes=float(N) * K * w.element_size()):
+        _lib.check(lib.iir_linear_small(_p(x), _dt(x), _p(w), _dt(w), _p(_f32c(bias, "bias")), _p(out),
+                                        _dt(out), M, N, K, act, _stream()), "iir_linear_small")
     return out
 
 

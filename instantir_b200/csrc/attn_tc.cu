@@ -2,12 +2,12 @@
 //
 //   out = sum_s seg_scale[s] * softmax(Q K_sᵀ * scale) V_s         (1 or 2 key segments)
 //
-// One CTA per (128-query tile, head, batch):
+// One CTA per (128-query tile, head, batch); TWO CTAs per SM (112 KiB smem, 256 TMEM columns each) so every
+// warp scheduler holds two softmax warps and one CTA's MMAs overlap the other's softmax:
 //   warp 0     : TMA producer — Q once, then (K_j, V_j) 128-key blocks, double buffered
 //   warp 1     : single-thread MMA issuer.  S_j = Q K_jᵀ (UMMA 128x128x16 x4) into one of two
-//                TMEM S buffers; O_j = P_j V_j (UMMA 128x64x16 x8, V as MN-major B operand) into one
-//                of two TMEM O buffers.  S_{j+1} is issued before P_j V_j so the tensor core works
-//                while the softmax warps are busy with block j.
+//                the TMEM S buffer; O_j = P_j V_j (UMMA 128x64x16 x8, V as MN-major B operand) into one
+//                of two TMEM O buffers.
 //   warps 2..5 : softmax — one query row per thread (TMEM lane == row, no shuffles): row max,
 //                exp2, row sum, P_j -> bf16 into 128B-swizzled smem (A operand of the PV MMA),
 //                then o = o*alpha + O_j read back from TMEM (accumulator kept in registers).
@@ -38,27 +38,28 @@ struct alignas(64) AttnTcParams {
   float scale_log2;  // softmax_scale * log2(e)
 };
 
+constexpr int ATT_TMEM_COLS = 256;  // S (128) + 2 x O (64): two CTAs share the SM's 512 columns
+
 template <int NSEG>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, NSEG == 1 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzle tiles need 1024-byte alignment
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
   uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;   // 2 buffers x 32 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  uint8_t* sP = sV + 2 * TILE_BYTES;   // 1 buffer x 32 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* kv_full = bars + 1;       // 2
   uint64_t* kv_empty = bars + 3;      // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* s_empty = bars + 7;       // 2
-  uint64_t* p_full = bars + 9;        // 2
-  uint64_t* p_empty = bars + 11;      // 2
-  uint64_t* o_full = bars + 13;       // 2
-  uint64_t* o_empty = bars + 15;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* s_full = bars + 5;        // 1
+  uint64_t* s_empty = bars + 6;       // 1
+  uint64_t* p_full = bars + 7;        // 1
+  uint64_t* p_empty = bars + 8;       // 1
+  uint64_t* o_full = bars + 9;        // 2
+  uint64_t* o_empty = bars + 11;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -69,25 +70,25 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
     tma_prefetch_desc(&p.tmK[0]);
     tma_prefetch_desc(&p.tmV[0]);
     mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&p_empty[s], 1);
       mbar_init(&o_full[s], 1);
       mbar_init(&o_empty[s], 128);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 2 x 64 columns
+  const uint32_t tmem_S = tmem_base;        // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;  // 2 x 64 columns
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -114,10 +115,10 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
       auto issue_pv = [&](int j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&p_full[st], ph);
+        mbar_wait(p_full, j & 1);
         mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP + st * 2 * TILE_BYTES);
+        const uint32_t pa = smem_u32(sP);
         const uint32_t va = smem_u32(sV + st * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -126,7 +127,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
           umma_bf16(tmem_O + st * 64, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
         }
         umma_commit(&kv_empty[st]);
-        umma_commit(&p_empty[st]);
+        umma_commit(p_empty);
         umma_commit(&o_full[st]);
       };
       mbar_wait(q_full, 0);
@@ -135,16 +136,16 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
         const int st = jb & 1;
         const uint32_t ph = (jb >> 1) & 1;
         mbar_wait(&kv_full[st], ph);
-        mbar_wait(&s_empty[st], ph ^ 1);
+        mbar_wait(s_empty, (jb & 1) ^ 1);
         tc_fence_after();
         const uint32_t ka = smem_u32(sK + st * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint64_t adesc = umma_desc_sw128(qa + k * 32, 16, 1024);
           uint64_t bdesc = umma_desc_sw128(ka + k * 32, 16, 1024);
-          umma_bf16(tmem_S + st * 128, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_S, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[st]);
+        umma_commit(s_full);
         if (jb > 0) issue_pv(jb - 1);
       }
       issue_pv(nb_total - 1);
@@ -192,9 +193,9 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
         const int st = jb & 1;
         const uint32_t ph = (jb >> 1) & 1;
         const int valid = min(128, p.kv_len[s] - jl * 128);
-        mbar_wait(&s_full[st], ph);
+        mbar_wait(s_full, jb & 1);
         tc_fence_after();
-        const uint32_t ts = tmem_S + trow + st * 128;
+        const uint32_t ts = tmem_S + trow;
         // pass 1: row max
         float mx = m_run;
 #pragma unroll 1
@@ -209,8 +210,8 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
         const float alpha = exp2f((m_run - mx) * sl2);
         const float mneg = -mx * sl2;
         // pass 2: P = exp2(S*sl2 - m*sl2) -> bf16 smem (swizzled K-major A operand), row sum
-        mbar_wait(&p_empty[st], ph ^ 1);
-        uint8_t* prow = sP + st * 2 * TILE_BYTES + row * 128;
+        mbar_wait(p_empty, (jb & 1) ^ 1);
+        uint8_t* prow = sP + row * 128;
         float sum = 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < 128; cc += 32) {
@@ -238,9 +239,9 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
           }
         }
         tc_fence_before();
-        mbar_arrive(&s_empty[st]);
+        mbar_arrive(s_empty);
         fence_async_smem();
-        mbar_arrive(&p_full[st]);
+        mbar_arrive(p_full);
         l_run = l_run * alpha + sum;
         m_run = mx;
         if (jb > seg_first) consume_o(jb - 1, alpha_prev);
@@ -283,7 +284,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
 }
 
@@ -337,7 +338,7 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   p.B = a->B; p.heads = a->heads; p.n_q = a->n_q;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
 
-  const size_t smem = 9 * TILE_BYTES + 1024 + 256;
+  const size_t smem = 7 * TILE_BYTES + 256;
   dim3 grid((a->n_q + 127) / 128, a->heads, a->B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;

@@ -148,6 +148,24 @@ void launch_gemm_simt(const GemmSimtParams& p, int pair, cudaStream_t st) {
   else gemm_simt_kernel<TA, TW, 2><<<grid, 256, 0, st>>>(p);
 }
 
+template <typename TW>
+__device__ __forceinline__ void ld8(const TW* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
 // ------------------------------------------------------------------- direct 3x3 conv (tiny C)
 // one thread per (pixel, cout); weights [Cout,3,3,Cin] fp32.
 template <typename TI, typename TO>
@@ -184,6 +202,74 @@ __global__ void conv3x3_direct_kernel(const TI* __restrict__ in, int in_nchw,
     st_f(out + ((static_cast<long long>(n) * Cout + co) * H + y) * W + x, acc);
   } else {
     st_f(out + ((static_cast<long long>(n) * out_H + out_row_off + y) * W + x) * Cout + co, acc);
+  }
+}
+
+// conv_out-type: NHWC input with many channels, tiny Cout (<= 8), NCHW or NHWC output.
+// One warp per 4 consecutive pixels of a row; lanes split the (tap, channel) reduction with 8-wide
+// vector loads, so each weight vector loaded is applied to 4 pixels.
+template <typename TI, typename TO, int CO>
+__global__ void __launch_bounds__(256)
+conv3x3_small_cout_kernel(const TI* __restrict__ in, const float* __restrict__ w,
+                          const float* __restrict__ bias, TO* __restrict__ out, int out_nchw, int n_img,
+                          int H, int W, int Cin, int out_H, int out_row_off) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = (W + 3) >> 2;
+  const long long gid = blockIdx.x * 8LL + warp;
+  if (gid >= static_cast<long long>(n_img) * H * wq) return;
+  const int xq = static_cast<int>(gid % wq);
+  const int y = static_cast<int>((gid / wq) % H);
+  const int n = static_cast<int>(gid / (static_cast<long long>(wq) * H));
+  const int x0 = xq * 4;
+  float acc[4][CO];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[p][c] = 0.f;
+  const int cv = Cin >> 3;
+  for (int i = lane; i < 9 * cv; i += 32) {
+    const int tap = i / cv, c8 = (i - tap * cv) * 8;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    float wv[CO][8];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) ld8<float>(w + (static_cast<long long>(c) * 9 + tap) * Cin + c8, wv[c]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int xx = x0 + p + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      float xv[8];
+      ld8<TI>(in + ((static_cast<long long>(n) * H + yy) * W + xx) * Cin + c8, xv);
+#pragma unroll
+      for (int c = 0; c < CO; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][c] = fmaf(xv[j], wv[c][j], acc[p][c]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      float v = acc[p][c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[p][c] = v;
+    }
+  if (lane < 4 * CO) {
+    const int p = lane / CO, c = lane - p * CO;
+    const int x = x0 + p;
+    if (x < W) {
+      float v = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int cc = 0; cc < CO; ++cc)
+          if (pp == p && cc == c) v = acc[pp][cc];
+      v += bias ? bias[c] : 0.f;
+      if (out_nchw) st_f(out + ((static_cast<long long>(n) * CO + c) * H + y) * W + x, v);
+      else st_f(out + ((static_cast<long long>(n) * out_H + out_row_off + y) * W + x) * CO + c, v);
+    }
   }
 }
 
@@ -245,28 +331,42 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnSimtParams p) 
 }
 
 // --------------------------------------------------------------------------- small-M linear
-// out[m, n] = act(sum_k x[m,k] w[n,k] + bias[n]); one warp per output column n, M <= 16.
-template <typename TX, typename TW, typename TO>
-__global__ void __launch_bounds__(256) linear_small_kernel(const TX* __restrict__ x,
+// out[m, n] = act(sum_k x[m,k] w[n,k] + bias[n]), M <= 16.  HBM-bound on the weight read: x is staged
+// in shared memory once per block, each warp streams one weight row with 16-byte loads.
+constexpr int LS_ROWS = 8;  // weight rows (one per warp) per block
+
+template <typename TW, typename TO, int MT>
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x,
                                                            const TW* __restrict__ w,
                                                            const float* __restrict__ bias,
                                                            TO* __restrict__ out, int M, int N, int K,
                                                            int act) {
+  extern __shared__ float xs[];  // [M][K]
+  for (int i = threadIdx.x * 4; i < M * K; i += 256 * 4)
+    *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(x + i);
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
+  const int n = blockIdx.x * LS_ROWS + warp;
   if (n >= N) return;
-  float acc[16];
+  float acc[MT];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
   const TW* wr = w + static_cast<long long>(n) * K;
-  for (int k = lane; k < K; k += 32) {
-    float wv = ld_f(wr + k);
+  for (int k = lane * 8; k < K; k += 256) {
+    float wv[8];
+    ld8<TW>(wr + k, wv);
 #pragma unroll
-    for (int m = 0; m < 16; ++m)
-      if (m < M) acc[m] = fmaf(ld_f(x + static_cast<long long>(m) * K + k), wv, acc[m]);
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        const float* xr = xs + m * K + k;
+        float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+        acc[m] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + b.x * wv[4] + b.y * wv[5] +
+                  b.z * wv[6] + b.w * wv[7];
+      }
+    }
   }
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
+  for (int m = 0; m < MT; ++m) {
     if (m < M) {
       float v = acc[m];
 #pragma unroll
@@ -328,9 +428,24 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
               "iir_conv3x3_direct: bad args");
   IIR_REQUIRE(out_nchw || (out_H >= H + out_row_off && out_row_off >= 0),
               "iir_conv3x3_direct: output window out of range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!in_nchw && Cout == 4 && Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    long long warps = static_cast<long long>(n_img) * H * ((W + 3) / 4);
+    int blocks8 = static_cast<int>((warps + 7) / 8);
+#define GOS(TI, TO)                                                                                 \
+  conv3x3_small_cout_kernel<TI, TO, 4><<<blocks8, 256, 0, st>>>(                                    \
+      reinterpret_cast<const TI*>(in), w, bias, reinterpret_cast<TO*>(out), out_nchw, n_img, H, W,  \
+      Cin, out_H, out_row_off)
+    if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GOS(float, float);
+    else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GOS(float, bf16);
+    else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GOS(bf16, float);
+    else GOS(bf16, bf16);
+#undef GOS
+    count_launch();
+    return check_launch("iir_conv3x3_direct");
+  }
   long long total = static_cast<long long>(n_img) * H * W * Cout;
   int blocks = static_cast<int>((total + 255) / 256);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define GO(TI, TO)                                                                               \
   conv3x3_direct_kernel<TI, TO><<<blocks, 256, 0, st>>>(                                         \
       reinterpret_cast<const TI*>(in), in_nchw, w, bias, reinterpret_cast<TO*>(out), out_nchw,   \
@@ -371,18 +486,41 @@ extern "C" int iir_linear_small(const void* x, int x_dtype, const void* w, int w
                                 int act, void* stream) {
   IIR_REQUIRE(x && w && out && M >= 1 && M <= 16 && N > 0 && K > 0,
               "iir_linear_small: need 1 <= M <= 16 (M=%d)", M);
-  int blocks = (N + 7) / 8;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define GO(TX, TW, TO)                                                                      \
-  linear_small_kernel<TX, TW, TO><<<blocks, 256, 0, st>>>(                                  \
-      reinterpret_cast<const TX*>(x), reinterpret_cast<const TW*>(w), bias,                 \
-      reinterpret_cast<TO*>(out), M, N, K, act)
   IIR_REQUIRE(x_dtype == IIR_F32, "iir_linear_small: x must be fp32");
-  if (w_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float, float);
-  else if (w_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(float, bf16, float);
-  else if (w_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, float, bf16);
-  else GO(float, bf16, bf16);
+  IIR_REQUIRE(K % 8 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "iir_linear_small: K=%d must be a multiple of 8 and x, w 16-byte aligned", K);
+  size_t smem = static_cast<size_t>(M) * K * sizeof(float);
+  IIR_REQUIRE(smem <= 200 * 1024, "iir_linear_small: M*K too large for shared memory");
+  int blocks = (N + LS_ROWS - 1) / LS_ROWS;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+#define GO2(TW, TO, MT)                                                                            \
+  do {                                                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      e = cudaFuncSetAttribute(linear_small_kernel<TW, TO, MT>,                                    \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    if (e == cudaSuccess)                                                                          \
+      linear_small_kernel<TW, TO, MT><<<blocks, 256, smem, st>>>(                                  \
+          reinterpret_cast<const float*>(x), reinterpret_cast<const TW*>(w), bias,                 \
+          reinterpret_cast<TO*>(out), M, N, K, act);                                               \
+  } while (0)
+#define GO(TW, TO)                   \
+  do {                               \
+    if (M <= 2) GO2(TW, TO, 2);      \
+    else if (M <= 4) GO2(TW, TO, 4); \
+    else GO2(TW, TO, 16);            \
+  } while (0)
+  if (w_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
+  else if (w_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else if (w_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
+  else GO(bf16, bf16);
 #undef GO
+#undef GO2
+  if (e != cudaSuccess) {
+    set_error("iir_linear_small: %s", cudaGetErrorString(e));
+    return IIR_ERR_CUDA;
+  }
   count_launch();
   return check_launch("iir_linear_small");
 }

@@ -65,14 +65,35 @@ def _f32c(t: Optional[torch.Tensor], name: str):
     return t
 
 
+N_SM = 148  # B200
+
+
 def default_bn(n: int, pair: bool = False) -> int:
-    """N-tile width: 256 when it divides N, else the largest multiple of 32 (64 when paired)
-    <= 256 that divides N; falls back to a masked 128-wide tile."""
+    """pack-time N-tile width for paired (GEGLU/SFT) weights: the largest multiple of 64 <= 256 that
+    divides N (their row interleave is fixed when the weights are packed)."""
     step = 64 if pair else 32
     for bn in range(256, step - 1, -step):
         if n % bn == 0:
             return bn
     return 128
+
+
+def choose_bn(M: int, N: int, K: int) -> int:
+    """Wave-aware N-tile width for the persistent tcgen05 GEMM (one CTA per SM, static round-robin
+    over 128 x BN tiles).  Cost model per tile: K/16 UMMA steps of max(BN/2, 32 + BN/4) cycles (tensor
+    pipe vs. shared-memory operand reads at 128 B/clk) + pipeline fill/drain and the exposed epilogue;
+    total = waves x tile cost.  A narrower tile often wins when 128 x 256 tiles would leave SMs idle
+    (e.g. M=2048, N=1280: 80 tiles on 148 SMs -> BN=160 gives 128 tiles of 0.625x the length)."""
+    tm = (M + 127) // 128
+    best, best_cost = 256, None
+    for bn in range(32, 257, 32):
+        tn = (N + bn - 1) // bn
+        waves = (tm * tn + N_SM - 1) // N_SM
+        cyc = max(bn / 2.0, 32.0 + bn / 4.0)
+        cost = waves * ((K / 16.0) * cyc + 400.0 + 3.0 * bn)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = bn, cost
+    return best
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
@@ -105,7 +126,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.out, g.out_dtype = _p(out), _dt(out)
     g.ld_out = ld_out if ld_out is not None else n_out
     g.act, g.pair = act, pair
-    g.bn = bn if bn is not None else default_bn(N, bool(pair))
+    g.bn = bn if bn is not None else (default_bn(N, True) if pair else choose_bn(M, N, K))
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
     with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K):

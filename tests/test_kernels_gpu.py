@@ -42,7 +42,8 @@ def pack_pairs(w, b, bn):
 # ------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 192, 320, 64), (1024, 640, 640, 128),
-                                      (2048, 1280, 1280, 256), (515, 320, 2560, 160)])
+                                      (2048, 1280, 1280, 256), (515, 320, 2560, 160), (1024, 3840, 640, 224),
+                                      (640, 1280, 320, 96), (2048, 1280, 1280, None), (4096, 640, 2560, None)])
 def test_gemm_linear(tc, M, N, K, bn):
     dt = torch.bfloat16 if tc else torch.float32
     a = rnd(M, K, seed=1, dtype=dt)
@@ -119,7 +120,7 @@ def _conv_ref(x_nhwc, w_packed, bias, stride=1, up2=False):
 
 
 @pytest.mark.parametrize("tc", [True, False])
-@pytest.mark.parametrize("n,H,W,Cin,Cout,bn", [(2, 16, 16, 64, 128, 128), (1, 32, 32, 128, 64, 64),
+@pytest.mark.parametrize("n,H,W,Cin,Cout,bn", [(2, 16, 16, 64, 128, 128), (1, 32, 32, 128, 64, 64), (2, 32, 32, 64, 320, None),
                                                (4, 8, 8, 64, 64, 64), (2, 64, 32, 64, 192, 64),
                                                (1, 8, 128, 64, 64, 64), (3, 8, 8, 128, 128, 128),
                                                (1, 12, 24, 64, 64, 64)])

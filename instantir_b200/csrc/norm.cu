@@ -6,7 +6,7 @@
 namespace iir {
 namespace {
 
-constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_MAX_CHUNKS = 256;
 constexpr int GN_THREADS = 256;
 
 // ---- stage 1: per (image, row-chunk) partial sum / sum of squares for every group ------------
@@ -51,6 +51,43 @@ gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, int HW, i
   }
 }
 
+// ---- stage 1b: fixed-order reduction of the chunk partials -> (mean, rstd) per (image, group) ----
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats, int groups,
+                   int nchunks, double count, float eps) {
+  // 8 sub-lanes per group each sum every 8th chunk, then the 8 sub-sums are combined in a fixed
+  // order: deterministic, and only nchunks/8 dependent adds deep.
+  __shared__ double sh_s[64][8], sh_q[64][8];
+  const int img = blockIdx.x;
+  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  for (int g0 = 0; g0 < groups; g0 += 32) {
+    const int gg = g0 + g;
+    double s = 0.0, q = 0.0;
+    if (gg < groups) {
+      for (int ch = sub; ch < nchunks; ch += 8) {
+        const float2 pp = *reinterpret_cast<const float2*>(
+            partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + ch) * groups + gg) * 2);
+        s += pp.x;
+        q += pp.y;
+      }
+      sh_s[g][sub] = s;
+      sh_q[g][sub] = q;
+    }
+    __syncthreads();
+    if (gg < groups && sub == 0) {
+      s = q = 0.0;
+      for (int k = 0; k < 8; ++k) { s += sh_s[g][k]; q += sh_q[g][k]; }
+      double mean = s / count;
+      double var = q / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      float* o = stats + (static_cast<long long>(img) * groups + gg) * 2;
+      o[0] = static_cast<float>(mean);
+      o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+  }
+}
+
 // ---- stage 2: normalise, affine, optional SiLU ---------------------------------------------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(GN_THREADS)
@@ -61,29 +98,14 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   extern __shared__ float sm[];  // [C] scale, [C] shift
   float* s_scale = sm;
   float* s_shift = sm + C;
-  __shared__ float s_mean[64], s_rstd[64];
   const int img = blockIdx.y;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
-    double s = 0.0, q = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const float* pp = partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + ch) * groups + g) * 2;
-      s += pp[0];
-      q += pp[1];
-    }
-    double n = static_cast<double>(HW) * cpg;
-    double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
-  __syncthreads();
+  const float* s_stats = partials + static_cast<long long>(img) * groups * 2;  // (mean, rstd) pairs
   for (int c = threadIdx.x; c < C; c += GN_THREADS) {
     int g = c / cpg;
-    float sc = s_rstd[g] * (gamma ? gamma[c] : 1.0f);
+    float sc = s_stats[2 * g + 1] * (gamma ? gamma[c] : 1.0f);
     s_scale[c] = sc;
-    s_shift[c] = (beta ? beta[c] : 0.0f) - s_mean[g] * sc;
+    s_shift[c] = (beta ? beta[c] : 0.0f) - s_stats[2 * g] * sc;
   }
   __syncthreads();
   const int cv = C >> 2;
@@ -109,7 +131,7 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
 // ---- LayerNorm: one warp per row, row cached in registers ----------------------------------
 constexpr int LN_MAX_V = 16;  // float4 per lane -> C <= 2048
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mod, int rows_per_sample,
@@ -119,10 +141,10 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   if (row >= rows) return;
   const int cv = C >> 2;
   const TI* xr = x + row * C;
-  float4 v[LN_MAX_V];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_V; ++j) {
+  for (int j = 0; j < NV; ++j) {
     int i = lane + 32 * j;
     if (i < cv) {
       v[j] = ld4(xr + i * 4);
@@ -134,7 +156,7 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   const float mean = s / C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_V; ++j) {
+  for (int j = 0; j < NV; ++j) {
     int i = lane + 32 * j;
     if (i < cv) {
       float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
@@ -153,7 +175,7 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   }
   TO* orow = out + row * C;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_V; ++j) {
+  for (int j = 0; j < NV; ++j) {
     int i = lane + 32 * j;
     if (i < cv) {
       float4 a = v[j];
@@ -184,7 +206,8 @@ using namespace iir;
 typedef __nv_bfloat16 bf16;
 
 extern "C" int64_t iir_groupnorm_scratch_floats(int n_img, int groups) {
-  return static_cast<int64_t>(n_img) * GN_MAX_CHUNKS * groups * 2;
+  // chunk partials followed by the finalised (mean, rstd) table
+  return static_cast<int64_t>(n_img) * GN_MAX_CHUNKS * groups * 2 + static_cast<int64_t>(n_img) * groups * 2;
 }
 
 extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta,
@@ -197,10 +220,10 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   IIR_REQUIRE(8 * C * sizeof(float) <= 200 * 1024, "iir_groupnorm: C=%d too large", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // enough chunks to fill the machine, at most GN_MAX_CHUNKS, at least 16 rows each
-  int want = (2 * sm_count() + n_img - 1) / n_img;
+  int want = (4 * sm_count() + n_img - 1) / n_img;
   int nchunks = want < 1 ? 1 : (want > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : want);
   int rpc = (HW + nchunks - 1) / nchunks;
-  if (rpc < 16) rpc = 16;
+  if (rpc < 8) rpc = 8;
   nchunks = (HW + rpc - 1) / rpc;
   size_t smem1 = 8 * (size_t)C * sizeof(float);
   dim3 g1(nchunks, n_img);
@@ -218,8 +241,14 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   count_launch();
   int rc = check_launch("iir_groupnorm(stats)");
   if (rc) return rc;
-  // apply: blocks of >= 8 rows, ~4 waves
-  int blocks_per_img = (4 * sm_count() + n_img - 1) / n_img;
+  float* stats = partials + static_cast<long long>(n_img) * GN_MAX_CHUNKS * groups * 2;
+  gn_finalize_kernel<<<n_img, 256, 0, st>>>(partials, stats, groups, nchunks,
+                                           static_cast<double>(HW) * (C / groups), eps);
+  count_launch();
+  rc = check_launch("iir_groupnorm(finalize)");
+  if (rc) return rc;
+  // apply: blocks of >= 8 rows, ~8 CTAs per SM
+  int blocks_per_img = (8 * sm_count() + n_img - 1) / n_img;
   int rpb = (HW + blocks_per_img - 1) / blocks_per_img;
   if (rpb < 8) rpb = 8;
   blocks_per_img = (HW + rpb - 1) / rpb;
@@ -227,7 +256,7 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   size_t smem2 = 2 * (size_t)C * sizeof(float);
 #define GO(TI, TO)                                                                                 \
   gn_apply_kernel<TI, TO><<<g2, GN_THREADS, smem2, st>>>(                                          \
-      reinterpret_cast<const TI*>(x), gamma, beta, partials, reinterpret_cast<TO*>(out), HW, C,    \
+      reinterpret_cast<const TI*>(x), gamma, beta, stats, reinterpret_cast<TO*>(out), HW, C,       \
       groups, nchunks, eps, silu, rpb)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
   else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
@@ -246,15 +275,23 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
   IIR_REQUIRE(!mod || rows_per_sample > 0, "iir_layernorm: mod needs rows_per_sample");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int blocks = (rows + 7) / 8;
-#define GO(TI, TO)                                                                              \
-  layernorm_kernel<TI, TO><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, \
-                                                   mod, rows_per_sample,                        \
-                                                   reinterpret_cast<TO*>(out), rows, C, eps)
+  const int nv = (C / 4 + 31) / 32;
+#define GO2(TI, TO, NV)                                                                                \
+  layernorm_kernel<TI, TO, NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, mod, \
+                                                       rows_per_sample, reinterpret_cast<TO*>(out), rows, C, eps)
+#define GO(TI, TO)                     \
+  do {                                 \
+    if (nv <= 2) GO2(TI, TO, 2);       \
+    else if (nv <= 5) GO2(TI, TO, 5);  \
+    else if (nv <= 10) GO2(TI, TO, 10);\
+    else GO2(TI, TO, 16);              \
+  } while (0)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
   else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
   else if (x_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
   else GO(bf16, bf16);
 #undef GO
+#undef GO2
   count_launch();
   return check_launch("iir_layernorm");
 }

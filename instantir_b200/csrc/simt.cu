@@ -205,6 +205,52 @@ __global__ void conv3x3_direct_kernel(const TI* __restrict__ in, int in_nchw,
   }
 }
 
+// conv_in-type: tiny Cin (<= 8), many output channels.  Weights are staged once per block in shared
+// memory transposed to [tap*Cin + c][Cout] so that consecutive threads (consecutive co) read
+// consecutive words; each block produces PIX pixels x Cout outputs with coalesced stores.
+constexpr int SC_PIX = 32;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+conv3x3_small_cin_kernel(const TI* __restrict__ in, int in_nchw, const float* __restrict__ w,
+                         const float* __restrict__ bias, TO* __restrict__ out, int n_img, int H, int W,
+                         int Cin, int Cout, int out_H, int out_row_off) {
+  extern __shared__ float ws[];  // [9*Cin][Cout] weights, then [SC_PIX][9*Cin] input patches
+  float* xs = ws + 9 * Cin * Cout;
+  const int kk = 9 * Cin;
+  for (int i = threadIdx.x; i < kk * Cout; i += 256) {
+    int co = i / kk, k = i - co * kk;  // source order [co][tap][c]
+    ws[k * Cout + co] = w[i];
+  }
+  const long long pix0 = blockIdx.x * static_cast<long long>(SC_PIX);
+  const long long npix = static_cast<long long>(n_img) * H * W;
+  for (int i = threadIdx.x; i < SC_PIX * kk; i += 256) {
+    int pp = i / kk, k = i - pp * kk;
+    long long pix = pix0 + pp;
+    float v = 0.f;
+    if (pix < npix) {
+      int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+      long long n = pix / (static_cast<long long>(W) * H);
+      int tap = k / Cin, c = k - tap * Cin;
+      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = in_nchw ? ld_f(in + ((n * Cin + c) * H + yy) * W + xx) : ld_f(in + ((n * H + yy) * W + xx) * Cin + c);
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SC_PIX * Cout; i += 256) {
+    int pp = i / Cout, co = i - pp * Cout;
+    long long pix = pix0 + pp;
+    if (pix >= npix) break;
+    float acc = bias ? bias[co] : 0.f;
+    const float* xr = xs + pp * kk;
+    for (int k = 0; k < kk; ++k) acc = fmaf(xr[k], ws[k * Cout + co], acc);
+    int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    long long n = pix / (static_cast<long long>(W) * H);
+    st_f(out + ((n * out_H + out_row_off + y) * W + x) * Cout + co, acc);
+  }
+}
+
 // conv_out-type: NHWC input with many channels, tiny Cout (<= 8), NCHW or NHWC output.
 // One warp per 4 consecutive pixels of a row; lanes split the (tap, channel) reduction with 8-wide
 // vector loads, so each weight vector loaded is applied to 4 pixels.
@@ -441,6 +487,33 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
     else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GOS(bf16, float);
     else GOS(bf16, bf16);
 #undef GOS
+    count_launch();
+    return check_launch("iir_conv3x3_direct");
+  }
+  if (!out_nchw && Cin <= 8 && (size_t)(9 * Cin) * (Cout + SC_PIX) * sizeof(float) <= 200 * 1024) {
+    size_t smem = (size_t)(9 * Cin) * (Cout + SC_PIX) * sizeof(float);
+    long long npix = static_cast<long long>(n_img) * H * W;
+    int blocksp = static_cast<int>((npix + SC_PIX - 1) / SC_PIX);
+    cudaError_t e = cudaSuccess;
+#define GOC(TI, TO)                                                                                   \
+  do {                                                                                                \
+    if (smem > 48 * 1024)                                                                             \
+      e = cudaFuncSetAttribute(conv3x3_small_cin_kernel<TI, TO>,                                      \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    if (e == cudaSuccess)                                                                             \
+      conv3x3_small_cin_kernel<TI, TO><<<blocksp, 256, smem, st>>>(                                   \
+          reinterpret_cast<const TI*>(in), in_nchw, w, bias, reinterpret_cast<TO*>(out), n_img, H, W, \
+          Cin, Cout, out_H, out_row_off);                                                             \
+  } while (0)
+    if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GOC(float, float);
+    else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GOC(float, bf16);
+    else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GOC(bf16, float);
+    else GOC(bf16, bf16);
+#undef GOC
+    if (e != cudaSuccess) {
+      set_error("iir_conv3x3_direct: %s", cudaGetErrorString(e));
+      return IIR_ERR_CUDA;
+    }
     count_launch();
     return check_launch("iir_conv3x3_direct");
   }

@@ -3,6 +3,7 @@
 // against cudart only and still loads — without computing — on a GPU-less build box).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -42,6 +43,15 @@ int sm_count() {
     }
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IIR_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

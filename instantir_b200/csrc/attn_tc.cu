@@ -60,6 +60,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   uint64_t* o_empty = bars + 11;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -87,6 +88,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const uint32_t tmem_S = tmem_base;        // 128 columns
   const uint32_t tmem_O = tmem_base + 128;  // 2 x 64 columns
 
@@ -344,10 +346,10 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   cudaError_t e;
   if (a->n_seg == 1) {
     e = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) attn_tc_kernel<1><<<grid, ATT_THREADS, smem, st>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(attn_tc_kernel<1>, grid, dim3(ATT_THREADS), smem, st, p);
   } else {
     e = cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) attn_tc_kernel<2><<<grid, ATT_THREADS, smem, st>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(attn_tc_kernel<2>, grid, dim3(ATT_THREADS), smem, st, p);
   }
   if (e != cudaSuccess) {
     set_error("iir_attn_tc: %s", cudaGetErrorString(e));

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/instantir_b200.h"
 
@@ -19,6 +20,27 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, c
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                       CUtensorMapSwizzle swz);
 int sm_count();
+bool pdl_enabled();
+
+// Launch with Programmatic Dependent Launch allowed: the kernel may start while its stream predecessor
+// is still draining; it must call pdl_wait() before touching memory the predecessor wrote.  Every kernel
+// of this library calls pdl_trigger() at entry so that ITS successor can be scheduled early.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define IIR_REQUIRE(cond, ...)          \
   do {                                  \
@@ -75,6 +97,12 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 __device__ __forceinline__ float gelu_erf_f(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
+
+// ---- Programmatic Dependent Launch ---------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -30,6 +30,8 @@ concat_inject_kernel(const void* h, int h_bf, int C1, const void* rh, int rh_bf,
                      int rows_per_sample, void* out, int out_bf, long long M) {
   const int cv1 = C1 >> 2, cv = (C1 + C2) >> 2;
   const long long total = M * cv;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     long long m = i / cv;
     int v = static_cast<int>(i - m * cv);
@@ -94,6 +96,8 @@ cast2d_kernel(const void* in, int in_bf, long long ld_in, void* out, int out_bf,
               long long rows, int cols) {
   const int cv = cols >> 2;
   const long long total = rows * cv;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     long long r = i / cv;
     int v = static_cast<int>(i - r * cv);
@@ -148,10 +152,10 @@ extern "C" int iir_concat_inject(const void* h, int h_dtype, int C1, const void*
   IIR_REQUIRE(!cond_scale || rows_per_sample > 0, "iir_concat_inject: rows_per_sample missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long work = M * ((C1 + C2) / 4);
-  concat_inject_kernel<<<grid_for(work), 256, 0, st>>>(
-      h, h_dtype == IIR_BF16, C1, rh, rh_dtype == IIR_BF16, skip, skip_dtype == IIR_BF16, C2, rs,
-      rs_dtype == IIR_BF16, cond_scale, rows_per_sample > 0 ? rows_per_sample : 1, out,
-      out_dtype == IIR_BF16, M);
+  launch_pdl(concat_inject_kernel, dim3(grid_for(work)), dim3(256), 0, st,
+      h, (int)(h_dtype == IIR_BF16), C1, rh, (int)(rh_dtype == IIR_BF16), skip, (int)(skip_dtype == IIR_BF16), C2, rs,
+      (int)(rs_dtype == IIR_BF16), cond_scale, rows_per_sample > 0 ? rows_per_sample : 1, out,
+      (int)(out_dtype == IIR_BF16), (long long)M);
   count_launch();
   return check_launch("iir_concat_inject");
 }
@@ -184,8 +188,8 @@ extern "C" int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out
   IIR_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0,
               "iir_cast2d: bad shape rows=%lld cols=%d", (long long)rows, cols);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cast2d_kernel<<<grid_for(rows * (cols / 4)), 256, 0, st>>>(in, in_dtype == IIR_BF16, ld_in, out,
-                                                             out_dtype == IIR_BF16, ld_out, rows, cols);
+  launch_pdl(cast2d_kernel, dim3(grid_for(rows * (cols / 4))), dim3(256), 0, st, in, (int)(in_dtype == IIR_BF16),
+             (long long)ld_in, out, (int)(out_dtype == IIR_BF16), (long long)ld_out, (long long)rows, cols);
   count_launch();
   return check_launch("iir_cast2d");
 }

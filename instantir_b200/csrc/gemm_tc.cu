@@ -7,8 +7,12 @@
 //   * warp 0      : TMA producer — A and W tiles land in 128B-swizzled smem stages
 //   * warp 1      : single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), accumulators in TMEM,
 //                   two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1
-//   * warps 2..5  : epilogue — tcgen05.ld rows out of TMEM, fused bias / temb row-vector /
-//                   SiLU / GEGLU / SFT / residual add, bf16 or fp32 store
+//   * warps 2..9  : epilogue — tcgen05.ld rows out of TMEM, fused bias / temb row-vector /
+//                   SiLU / GEGLU / SFT / residual add, bf16 or fp32 store.  Two warps per TMEM lane
+//                   quarter take alternate 32-column chunks, halving the exposed epilogue of
+//                   single-wave problems
+//   * Programmatic Dependent Launch: barrier init / TMEM alloc / descriptor prefetch overlap the
+//     previous kernel's tail; global memory is touched only after griddepcontrol.wait
 //   * conv mode   : the A tile is a (Nt x Ht x Wt) pixel box of an NHWC tensor fetched with a 4-D
 //                   TMA map at the tap offset (kx-1, ky-1); out-of-bounds box elements are
 //                   zero-filled by TMA, which *is* the conv's zero padding. No im2col buffer.
@@ -24,7 +28,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 
@@ -91,6 +95,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -101,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], 256);
     }
     fence_mbar_init();
   }
@@ -110,6 +115,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the predecessor; its results are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -171,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int lane_base = (warp & 3) * 32;  // TMEM lane quarter this warp may access
+    const int chunk_par = (warp - 2) >> 2;   // which of the two warps of this quarter: odd/even chunks
     const int row = lane_base + lane;
     const int half = p.BN >> 1;
     const int n_out_total = PAIR ? (p.N >> 1) : p.N;
@@ -200,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
       const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
       const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
-      for (int cc = 0; cc < ncols; cc += 32) {
+      for (int cc = chunk_par * 32; cc < ncols; cc += 64) {
         uint32_t r[32];
         uint32_t r2[32];
         tmem_ld32(taddr + cc, r);
@@ -433,7 +440,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
 #define LAUNCH(PAIRV)                                                                              \
   e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                            (int)smem);                                                             \
-  if (e == cudaSuccess) gemm_tc_kernel<PAIRV><<<grid, GEMM_THREADS, smem, st>>>(p);
+  if (e == cudaSuccess) e = launch_pdl(gemm_tc_kernel<PAIRV>, dim3(grid), dim3(GEMM_THREADS), smem, st, p);
   if (a->pair == IIR_PAIR_NONE) { LAUNCH(0) }
   else if (a->pair == IIR_PAIR_GEGLU) { LAUNCH(1) }
   else if (a->pair == IIR_PAIR_SFT) { LAUNCH(2) }

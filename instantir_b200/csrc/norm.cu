@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, int HW, int C, int groups,
                 int rows_per_chunk) {
   extern __shared__ float sm[];  // [4][C] sums, [4][C] squares
+  pdl_trigger();
+  pdl_wait();
   float* s_sum = sm;
   float* s_sq = sm + 4 * C;
   const int chunk = blockIdx.x, img = blockIdx.y;
@@ -58,6 +60,8 @@ gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats
   // 8 sub-lanes per group each sum every 8th chunk, then the 8 sub-sums are combined in a fixed
   // order: deterministic, and only nchunks/8 dependent adds deep.
   __shared__ double sh_s[64][8], sh_q[64][8];
+  pdl_trigger();
+  pdl_wait();
   const int img = blockIdx.x;
   const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
   for (int g0 = 0; g0 < groups; g0 += 32) {
@@ -96,6 +100,8 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                 TO* __restrict__ out, int HW, int C, int groups, int nchunks, float eps, int silu,
                 int rows_per_block) {
   extern __shared__ float sm[];  // [C] scale, [C] shift
+  pdl_trigger();
+  pdl_wait();
   float* s_scale = sm;
   float* s_shift = sm + C;
   const int img = blockIdx.y;
@@ -138,6 +144,8 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                  TO* __restrict__ out, int rows, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + warp;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const int cv = C >> 2;
   const TI* xr = x + row * C;
@@ -231,19 +239,20 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   if (x_dtype == IIR_F32) {
     if (smem1 > 48 * 1024)
       e = cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    gn_stats_kernel<float><<<g1, GN_THREADS, smem1, st>>>(reinterpret_cast<const float*>(x), partials, HW, C, groups, rpc);
+    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<float>, g1, dim3(GN_THREADS), smem1, st, reinterpret_cast<const float*>(x), partials, HW, C, groups, rpc);
   } else {
     if (smem1 > 48 * 1024)
       e = cudaFuncSetAttribute(gn_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    gn_stats_kernel<bf16><<<g1, GN_THREADS, smem1, st>>>(reinterpret_cast<const bf16*>(x), partials, HW, C, groups, rpc);
+    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<bf16>, g1, dim3(GN_THREADS), smem1, st, reinterpret_cast<const bf16*>(x), partials, HW, C, groups, rpc);
   }
   if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   int rc = check_launch("iir_groupnorm(stats)");
   if (rc) return rc;
   float* stats = partials + static_cast<long long>(n_img) * GN_MAX_CHUNKS * groups * 2;
-  gn_finalize_kernel<<<n_img, 256, 0, st>>>(partials, stats, groups, nchunks,
-                                           static_cast<double>(HW) * (C / groups), eps);
+  e = launch_pdl(gn_finalize_kernel, dim3(n_img), dim3(256), 0, st, (const float*)partials, stats, groups, nchunks,
+                 static_cast<double>(HW) * (C / groups), eps);
+  if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   rc = check_launch("iir_groupnorm(finalize)");
   if (rc) return rc;
@@ -255,8 +264,8 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   dim3 g2(blocks_per_img, n_img);
   size_t smem2 = 2 * (size_t)C * sizeof(float);
 #define GO(TI, TO)                                                                                 \
-  gn_apply_kernel<TI, TO><<<g2, GN_THREADS, smem2, st>>>(                                          \
-      reinterpret_cast<const TI*>(x), gamma, beta, stats, reinterpret_cast<TO*>(out), HW, C,       \
+  e = launch_pdl(gn_apply_kernel<TI, TO>, g2, dim3(GN_THREADS), smem2, st,                        \
+      reinterpret_cast<const TI*>(x), gamma, beta, (const float*)stats, reinterpret_cast<TO*>(out), HW, C, \
       groups, nchunks, eps, silu, rpb)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
   else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
@@ -277,8 +286,8 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
   int blocks = (rows + 7) / 8;
   const int nv = (C / 4 + 31) / 32;
 #define GO2(TI, TO, NV)                                                                                \
-  layernorm_kernel<TI, TO, NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta, mod, \
-                                                       rows_per_sample, reinterpret_cast<TO*>(out), rows, C, eps)
+  launch_pdl(layernorm_kernel<TI, TO, NV>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const TI*>(x), gamma, beta, mod, \
+             rows_per_sample, reinterpret_cast<TO*>(out), rows, C, eps)
 #define GO(TI, TO)                     \
   do {                                 \
     if (nv <= 2) GO2(TI, TO, 2);       \

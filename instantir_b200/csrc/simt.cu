@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
                                                            TO* __restrict__ out, int M, int N, int K,
                                                            int act) {
   extern __shared__ float xs[];  // [M][K]
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x * 4; i < M * K; i += 256 * 4)
     *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(x + i);
   __syncthreads();
@@ -574,7 +576,7 @@ extern "C" int iir_linear_small(const void* x, int x_dtype, const void* w, int w
       e = cudaFuncSetAttribute(linear_small_kernel<TW, TO, MT>,                                    \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e == cudaSuccess)                                                                          \
-      linear_small_kernel<TW, TO, MT><<<blocks, 256, smem, st>>>(                                  \
+      e = launch_pdl(linear_small_kernel<TW, TO, MT>, dim3(blocks), dim3(256), smem, st,           \
           reinterpret_cast<const float*>(x), reinterpret_cast<const TW*>(w), bias,                 \
           reinterpret_cast<TO*>(out), M, N, K, act);                                               \
   } while (0)

@@ -172,7 +172,7 @@ def run_reference(args):
             "cpu_baseline": {"value": img_s, "unit": "img/s", "cores": threads, "kind": "port",
                              "sample": f"UNet forward, 1 CFG branch, latent {latent}: {dt:.2f} s mean of {len(times)}"},
             "e2e": {"value": img_s, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------- GPU arm
@@ -224,6 +224,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     torch.set_grad_enabled(False)
 
@@ -362,13 +363,35 @@ def run_ours(args):
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Library banners (e.g. NCCL's version line) are written to fd 1 from C code.  Point fd 1 at stderr for
+    the duration of the run and keep the real stdout for the single JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

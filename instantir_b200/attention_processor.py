@@ -40,7 +40,12 @@ class CtxCache:
         key = _key(tensor)
         if self.valid.get(slot) == key:
             return self.buf[slot]
-        out = make(self.buf.get(slot))
+        out = make(self.buf.get((slot, key[1])))  # reuse a buffer only for the same conditioning shape
+        # the kernels wrote `out` through raw pointers: tell torch, so that caches keyed on `out`
+        # downstream (e.g. image K/V keyed on the Resampler tokens) see a new version
+        for t in (out if isinstance(out, (list, tuple)) else [out]):
+            torch.autograd.graph.increment_version(t)
+        self.buf[(slot, key[1])] = out
         self.buf[slot], self.valid[slot], self.keep[slot] = out, key, tensor
         return out
 

@@ -162,6 +162,40 @@ def test_full_step_config1_bf16_coarse_schedule():
         assert rel_l2(a, b) < 5e-2, f"step {i}"
 
 
+def test_batch_of_two_images_fp32():
+    """B = 2 images (CFG batch 4): every per-sample structure (temb row-vectors, adaLN, cond_scale,
+    per-image GroupNorm, multi-image conv tiles) vs the oracle."""
+    ref, rec_o, out, rec_p = _run_pair("fp32", B=2, graph=True)
+    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+        assert rel_l2(a, b) < 1e-4, f"step {i}"
+
+
+def test_repeated_calls_reuse_graphs_and_stay_correct_fp32():
+    """a second image through the same pipeline object (cached static buffers + CUDA graphs, context
+    caches refreshed in place) must be restored as correctly as the first."""
+    oc = ocfg.tiny()
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=8.0)
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = _pcfg_from(oc)
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=8.0 / oc.lora_rank), DEV, "fp32")
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, "fp32")
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+    for seed, B in ((1234, 1), (99, 1), (7, 2), (1234, 1)):
+        inp = make_inputs(oc, B=B, h=32, w=32, seed=seed)
+        kw = dict(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                  pooled_prompt_embeds=inp["pooled_prompt_embeds"],
+                  negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"], num_inference_steps=2,
+                  guidance_scale=7.0, preview_start=0.0)
+        ref = opipe.restore_latents(ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+                                    ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"],
+                                    generator=torch.Generator().manual_seed(5), **kw)
+        out = pipe(image=inp["image"], ip_adapter_image_embeds=[inp["ip"]], previewer_scheduler=LCMSingleStepScheduler(),
+                   generator=torch.Generator().manual_seed(5), **kw).images
+        torch.cuda.synchronize()
+        assert rel_l2(out, ref) < 1e-4, (seed, B)
+
+
 def test_step_shapes_no_preview_and_unet_only_fp32():
     """preview_start=1 (aggregator fed the LQ latent) and control_guidance_end=0.5 (second step UNet-only)."""
     ref, rec_o, out, rec_p = _run_pair("fp32", preview_start=1.0, cge=0.5, graph=True)

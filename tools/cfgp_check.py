@@ -46,5 +46,6 @@ res = torch.tensor([e_cfgp, e_dp], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"MULTI_GPU_CHECK precision={prec} cfg_parallel_vs_single={float(res[0]):.3e} dp_shard_vs_batched={float(res[1]):.3e}")
-    assert float(res[0]) < 1e-5 and float(res[1]) < 1e-5
+    tol = 1e-5 if prec == "fp32" else 2e-2  # bf16: different batch partition -> different tiles/rounding
+    assert float(res[0]) < tol and float(res[1]) < tol
 dist.barrier(); dist.destroy_process_group()

@@ -5,12 +5,15 @@
 // One CTA per (128-query tile, head, batch); TWO CTAs per SM (112 KiB smem, 256 TMEM columns each) so every
 // warp scheduler holds two softmax warps and one CTA's MMAs overlap the other's softmax:
 //   warp 0     : TMA producer — Q once, then (K_j, V_j) 128-key blocks, double buffered
-//   warp 1     : single-thread MMA issuer.  S_j = Q K_jᵀ (UMMA 128x128x16 x4) into one of two
-//                the TMEM S buffer; O_j = P_j V_j (UMMA 128x64x16 x8, V as MN-major B operand) into one
-//                of two TMEM O buffers.
-//   warps 2..5 : softmax — one query row per thread (TMEM lane == row, no shuffles): row max,
-//                exp2, row sum, P_j -> bf16 into 128B-swizzled smem (A operand of the PV MMA),
-//                then o = o*alpha + O_j read back from TMEM (accumulator kept in registers).
+//   warp 1     : single-thread MMA issuer.  S_j = Q K_jᵀ (UMMA 128x128x16 x4) into the TMEM S buffer;
+//                O += P_j V_j (UMMA 128x64x16 x8, V as MN-major B operand) ACCUMULATES in TMEM.
+//   warps 2..5 : softmax — one query row per thread (TMEM lane == row, no shuffles).  The whole S row
+//                is pulled into registers in one pass and the S buffer is released immediately, so
+//                Q K_{j+1}ᵀ runs under the softmax of block j.  exp2 is taken relative to a reference
+//                max that is only advanced (and O / l rescaled in TMEM, warp-uniformly) when the row max
+//                grows by more than 2^8 — the usual case after the first blocks is "no rescale", which
+//                removes the per-block O read-modify-write of a classic flash loop.  P_j -> bf16 into
+//                128B-swizzled smem (A operand of the PV MMA).
 // Two segments = decoupled text + image cross-attention with independent softmaxes
 // (module/ip_adapter/attention_processor.py:1165-1192); one segment = self-attention (:394-396).
 #include "common.cuh"
@@ -56,9 +59,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   uint64_t* s_empty = bars + 6;       // 1
   uint64_t* p_full = bars + 7;        // 1
   uint64_t* p_empty = bars + 8;       // 1
-  uint64_t* o_full = bars + 9;        // 2
-  uint64_t* o_empty = bars + 11;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   pdl_trigger();
 
@@ -78,8 +79,6 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&o_empty[s], 128);
     }
     fence_mbar_init();
   }
@@ -90,7 +89,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   const uint32_t tmem_S = tmem_base;        // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;  // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 128;  // 64 columns, accumulated across key blocks
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -114,23 +113,22 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      const int seg1_first = p.nblk[0];  // first flat block index of the second segment
       auto issue_pv = [&](int j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
         mbar_wait(p_full, j & 1);
-        mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP);
         const uint32_t va = smem_u32(sV + st * TILE_BYTES);
+        const bool fresh = (j == 0) || (NSEG > 1 && j == seg1_first);  // first block of a segment
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t adesc = umma_desc_sw128(pa + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
           uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
-          umma_bf16(tmem_O + st * 64, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_O, adesc, bdesc, idesc_pv, (k != 0 || !fresh) ? 1u : 0u);
         }
         umma_commit(&kv_empty[st]);
-        umma_commit(p_empty);
-        umma_commit(&o_full[st]);
+        umma_commit(p_empty);  // PV_j retired: P buffer free and O stable
       };
       mbar_wait(q_full, 0);
       const uint32_t qa = smem_u32(sQ);
@@ -158,126 +156,131 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
     const int row = lane_base + lane;
     const uint32_t trow = static_cast<uint32_t>(lane_base) << 16;
     const float sl2 = p.scale_log2;
-    float out_acc[64];
+    const float kLazy = 8.0f / sl2;  // advance the reference max only when exp2 arguments would exceed 8
+    float out_acc[NSEG > 1 ? 64 : 1];
     if (NSEG > 1) {
 #pragma unroll
       for (int d = 0; d < 64; ++d) out_acc[d] = 0.f;
     }
-    float o_acc[64];
+    uint8_t* prow = sP + row * 128;
+    const int qi = q0 + row;
+    bf16* optr = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
     int jb = 0;
 #pragma unroll 1
     for (int s = 0; s < NSEG; ++s) {
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o_acc[d] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-      const int seg_first = jb;
-
-      auto consume_o = [&](int j, float alpha) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&o_full[st], ph);
-        tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(tmem_O + trow + st * 64 + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int d = 0; d < 32; ++d)
-            o_acc[half * 32 + d] = fmaf(o_acc[half * 32 + d], alpha, __uint_as_float(r[d]));
-        }
-        tc_fence_before();
-        mbar_arrive(&o_empty[st]);
-      };
-
+      float m_ref = -INFINITY, l_run = 0.f;
 #pragma unroll 1
       for (int jl = 0; jl < p.nblk[s]; ++jl, ++jb) {
-        const int st = jb & 1;
-        const uint32_t ph = (jb >> 1) & 1;
         const int valid = min(128, p.kv_len[s] - jl * 128);
         mbar_wait(s_full, jb & 1);
         tc_fence_after();
-        const uint32_t ts = tmem_S + trow;
-        // pass 1: row max
-        float mx = m_run;
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(ts + cc, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cc + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+        uint32_t sr[128];
+        {
+          uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[0]);
+          uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[32]);
+          uint32_t (&a2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[64]);
+          uint32_t (&a3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[96]);
+          tmem_ld32(tmem_S + trow, a0);
+          tmem_ld32(tmem_S + trow + 32, a1);
+          tmem_ld32(tmem_S + trow + 64, a2);
+          tmem_ld32(tmem_S + trow + 96, a3);
         }
-        const float alpha = exp2f((m_run - mx) * sl2);
-        const float mneg = -mx * sl2;
-        // pass 2: P = exp2(S*sl2 - m*sl2) -> bf16 smem (swizzled K-major A operand), row sum
-        mbar_wait(p_empty, (jb & 1) ^ 1);
-        uint8_t* prow = sP + row * 128;
-        float sum = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(ts + cc, r);
-          tmem_ld_wait();
-          float pv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float e = exp2f(fmaf(__uint_as_float(r[j]), sl2, mneg));
-            pv[j] = (cc + j < valid) ? e : 0.f;
-            sum += pv[j];
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = cc + g * 8;          // first key column of this 16-byte chunk
-            const int panel = c >> 6;
-            const int q8 = (c & 63) >> 3;
-            uint4 u;
-            u.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]);
-            u.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
-            u.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]);
-            u.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(prow + panel * TILE_BYTES + ((q8 ^ (row & 7)) << 4)) = u;
-          }
-        }
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(s_empty);
-        fence_async_smem();
-        mbar_arrive(p_full);
-        l_run = l_run * alpha + sum;
-        m_run = mx;
-        if (jb > seg_first) consume_o(jb - 1, alpha_prev);
-        alpha_prev = alpha;
-      }
-      consume_o(jb - 1, alpha_prev);
-      const float w = p.seg_scale[s] / l_run;
-      if (NSEG > 1) {
+        mbar_arrive(s_empty);  // S is in registers: Q K_{j+1}^T may overwrite the TMEM buffer now
+        if (valid < 128) {
 #pragma unroll
-        for (int d = 0; d < 64; ++d) out_acc[d] = fmaf(o_acc[d], w, out_acc[d]);
-      } else {
-#pragma unroll
-        for (int d = 0; d < 64; ++d) o_acc[d] *= w;
-      }
-    }
-    const int qi = q0 + row;
-    if (qi < p.n_q) {
-      bf16* o = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
-#pragma unroll
-      for (int d = 0; d < 64; d += 8) {
-        uint4 u;
-        if (NSEG > 1) {
-          u.x = pack_bf16(out_acc[d], out_acc[d + 1]);
-          u.y = pack_bf16(out_acc[d + 2], out_acc[d + 3]);
-          u.z = pack_bf16(out_acc[d + 4], out_acc[d + 5]);
-          u.w = pack_bf16(out_acc[d + 6], out_acc[d + 7]);
-        } else {
-          u.x = pack_bf16(o_acc[d], o_acc[d + 1]);
-          u.y = pack_bf16(o_acc[d + 2], o_acc[d + 3]);
-          u.z = pack_bf16(o_acc[d + 4], o_acc[d + 5]);
-          u.w = pack_bf16(o_acc[d + 6], o_acc[d + 7]);
+          for (int j = 0; j < 128; ++j)
+            if (j >= valid) sr[j] = 0xff800000u;  // -inf
         }
-        *reinterpret_cast<uint4*>(o + d) = u;
+        // 8 independent chains instead of one 128-deep dependent chain
+        float mxs[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxs[c] = __uint_as_float(sr[c]);
+#pragma unroll
+        for (int j = 8; j < 128; j += 8)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(sr[j + c]));
+        const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                               fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+        // previous P V must have retired before P is overwritten / O is touched
+        mbar_wait(p_empty, (jb & 1) ^ 1);
+        tc_fence_after();
+        const bool first = (jl == 0);
+        const bool grow = !first && (mx > m_ref + kLazy);
+        if (first) m_ref = mx;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare: rescale O (TMEM) and l by exp2((m_ref - mx) * sl2) for the rows that need it
+          const float alpha = grow ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
+          if (grow) { l_run *= alpha; m_ref = mx; }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(tmem_O + trow + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) r[d] = __float_as_uint(__uint_as_float(r[d]) * alpha);
+            tmem_st32(tmem_O + trow + half * 32, r);
+          }
+          tmem_st_wait();
+        }
+        const float mneg = -m_ref * sl2;
+        float sums[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sums[c] = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          float e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            e[j] = ex2_approx(fmaf(__uint_as_float(sr[g * 8 + j]), sl2, mneg));
+            sums[j] += e[j];
+          }
+          const int panel = g >> 3;  // 64 keys per 128-byte panel row
+          const int q8 = g & 7;
+          uint4 u;
+          u.x = pack_bf16(e[0], e[1]);
+          u.y = pack_bf16(e[2], e[3]);
+          u.z = pack_bf16(e[4], e[5]);
+          u.w = pack_bf16(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + panel * TILE_BYTES + ((q8 ^ (row & 7)) << 4)) = u;
+        }
+        const float sum = ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
+        l_run += sum;
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
       }
+      // segment done: wait for its last P V, then O / l
+      mbar_wait(p_empty, (jb - 1) & 1);
+      tc_fence_after();
+      const float w = p.seg_scale[s] / l_run;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(tmem_O + trow + half * 32, r);
+        tmem_ld_wait();
+        if (NSEG > 1) {
+#pragma unroll
+          for (int d = 0; d < 32; ++d) out_acc[half * 32 + d] = fmaf(__uint_as_float(r[d]), w, out_acc[half * 32 + d]);
+        }
+        if (s == NSEG - 1 && qi < p.n_q) {
+#pragma unroll
+          for (int d = 0; d < 32; d += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j] = NSEG > 1 ? out_acc[half * 32 + d + j] : __uint_as_float(r[d + j]) * w;
+            uint4 u;
+            u.x = pack_bf16(v[0], v[1]);
+            u.y = pack_bf16(v[2], v[3]);
+            u.z = pack_bf16(v[4], v[5]);
+            u.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(optr + half * 32 + d) = u;
+          }
+        }
+      }
+      tc_fence_before();
     }
   }
 

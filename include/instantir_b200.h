@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 1
+#define IIR_ABI_VERSION 2
 
 typedef enum {
   IIR_OK = 0,
@@ -75,6 +75,8 @@ typedef struct {
   int act;              /* iir_act applied to (acc + bias + rowvec)                       */
   int pair;             /* iir_pair                                                       */
   int bn;               /* N tile (multiple of 32, <=256; multiple of 64 when paired)     */
+  int cluster;          /* tc: 0 = automatic, 1 = one CTA per tile, 2 = CTA pair (cta_group::2,
+                           256 x bn tile, each CTA stages half of the weight tile)         */
 } iir_gemm_args;
 
 /* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */

@@ -42,7 +42,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("res_dtype", C.c_int), ("ld_res", C.c_int64),
         ("aux", C.c_void_p), ("aux_dtype", C.c_int), ("ld_aux", C.c_int64),
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("ld_out", C.c_int64),
-        ("act", C.c_int), ("pair", C.c_int), ("bn", C.c_int),
+        ("act", C.c_int), ("pair", C.c_int), ("bn", C.c_int), ("cluster", C.c_int),
     ]
 
 
@@ -117,8 +117,8 @@ def load(build_if_missing: bool = True):
         except OSError as e:  # pragma: no cover
             raise IIRError(f"cannot load {LIB_PATH}: {e}") from e
         _declare(lib)
-        if lib.iir_abi_version() != 1:
-            raise IIRError(f"ABI version mismatch: library {lib.iir_abi_version()}, binding 1")
+        if lib.iir_abi_version() != 2:
+            raise IIRError(f"ABI version mismatch: library {lib.iir_abi_version()}, binding 2")
         _lib = lib
         return _lib
 

@@ -13,12 +13,27 @@
 //                   single-wave problems
 //   * Programmatic Dependent Launch: barrier init / TMEM alloc / descriptor prefetch overlap the
 //     previous kernel's tail; global memory is touched only after griddepcontrol.wait
+//   * clusters    : CL (1/2/4) CTAs that work on the same N tile (consecutive M tiles) form a cluster;
+//                   each fetches 1/CL of the weight tile and TMA-multicasts it to its peers, cutting
+//                   the L2->SM traffic that bounds a 128 x 256 tile (48 KB per 64-deep k-block) to
+//                   16 + 32/CL KB.  MMAs stay cta_group::1; a stage is refilled only after the MMAs of
+//                   ALL cluster CTAs retired it (multicast tcgen05.commit onto every CTA's empty barrier)
+//   * CTA pairs   : MMA2 = cta_group::2.  A 128 x 256 tile on one SM needs 192 B/clk of shared-memory
+//                   traffic (TMA writes + UMMA operand reads share the 128 B/clk port) = 67 % of the tensor
+//                   peak — measured 1165 of a predicted 1172 TFLOP/s.  A CTA pair computes a 256 x BN
+//                   tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader; each CTA stages
+//                   its own 128 A rows and only HALF of the weight tile, i.e. 128 B/clk.  Both CTAs' TMA
+//                   loads signal the leader's full barrier; the leader's commits are multicast to both
+//                   CTAs' empty / accumulator-full barriers; both epilogues arrive on the leader's
+//                   accumulator-empty barrier.
 //   * conv mode   : the A tile is a (Nt x Ht x Wt) pixel box of an NHWC tensor fetched with a 4-D
 //                   TMA map at the tap offset (kx-1, ky-1); out-of-bounds box elements are
 //                   zero-filled by TMA, which *is* the conv's zero padding. No im2col buffer.
 //
 // Replaces: nn.Linear / nn.Conv2d + following elementwise ops of the reference
 // (module/min_sdxl.py:246-283,301-307,502-523,569-573; module/aggregator.py:63-90).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace iir {
@@ -34,11 +49,12 @@ constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buf
 
 struct alignas(64) GemmTcParams {
   CUtensorMap tmA;
-  CUtensorMap tmB;
+  CUtensorMap tmB;  // box {64, BN / CL}
   int M, N, K, num_kb;
   int conv, n_img, H, W, Cin;
   int Wt, Ht, Nt, tiles_x, tiles_y, tiles_img;
   int tiles_m, tiles_n, BN, stages;
+  int tiles_m_cl;  // ceil(tiles_m / CL): M super-tiles per N tile
   const float* bias;
   const float* rowvec;
   int rows_per_sample;
@@ -60,10 +76,13 @@ struct TileCoord {
   int n0;          // first weight row (column of the packed output)
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int tile) {
+// super-tile index -> coordinates of this CTA's 128 x BN tile (CTA `rank` of the cluster takes the
+// rank-th M tile of the super-tile; it may lie past the matrix end: TMA zero-fills, stores are masked)
+template <int CL>
+__device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int stile, int rank) {
   TileCoord c;
-  int tn = tile / p.tiles_m;
-  int tm = tile - tn * p.tiles_m;
+  int tn = stile / p.tiles_m_cl;
+  int tm = (stile - tn * p.tiles_m_cl) * CL + rank;
   c.n0 = tn * p.BN;
   c.m0 = tm * BM;
   c.n_img0 = c.y0 = c.x0 = 0;
@@ -79,13 +98,15 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int tile)
   return c;
 }
 
-template <int PAIR>
+template <int PAIR, int CL, bool MMA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+  static_assert(!MMA2 || CL == 2, "cta_group::2 needs a 2-CTA cluster");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  // MMA2: each CTA of the pair stages only its half of the weight tile
+  const int stage_bytes = A_STAGE_BYTES + (MMA2 ? p.BN / 2 : p.BN) * BK * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
@@ -94,7 +115,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m_cl * p.tiles_n;            // super-tiles
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
   pdl_trigger();
 
   if (warp == 0 && lane == 0) {
@@ -102,19 +126,25 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      // multicast variant: one arrival per cluster CTA whose MMAs read this stage; MMA2: the leader's
+      // single commit is multicast to both CTAs
+      mbar_init(&empty_bar[s], MMA2 ? 1 : CL);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 256);
+      mbar_init(&tempty_bar[b], MMA2 ? 512 : 256);  // MMA2: both CTAs' epilogues arrive on the leader's
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (MMA2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives
   pdl_wait();  // everything above overlapped the predecessor; its results are visible from here on
 
   if (warp == 0) {
@@ -123,12 +153,28 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       int stage = 0;
       uint32_t phase = 0;
       const int cpb = p.conv ? p.Cin / BK : 1;  // 64-channel blocks per filter tap
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        TileCoord c = tile_coord(p, tile);
+      const int b_rows = p.BN / CL;  // weight rows this CTA fetches (and multicasts)
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        TileCoord c = tile_coord<CL>(p, tile, rank);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if (MMA2) {
+            // both CTAs' loads complete_tx on the leader's barrier: it expects 2 x stage_bytes
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+            if (p.conv) {
+              int tap = kb / cpb;
+              int cb = kb - tap * cpb;
+              int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_2sm(sa, &p.tmA, &full_bar[stage], cb * BK, c.x0 + kx - 1, c.y0 + ky - 1, c.n_img0);
+            } else {
+              tma_load_2d_2sm(sa, &p.tmA, &full_bar[stage], kb * BK, c.m0);
+            }
+            tma_load_2d_2sm(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0 + rank * b_rows);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           if (p.conv) {
             int tap = kb / cpb;
@@ -139,19 +185,23 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           } else {
             tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BK, c.m0);
           }
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0);
+          if (CL > 1)
+            tma_load_2d_mcast(sb + rank * b_rows * (BK * 2), &p.tmB, &full_bar[stage], kb * BK,
+                              c.n0 + rank * b_rows, kMask);
+          else
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, p.BN, 0, 0);
+    if (lane == 0 && (!MMA2 || rank == 0)) {
+      const uint32_t idesc = umma_idesc_bf16(MMA2 ? 2 * BM : BM, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_i = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_i) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
         const uint32_t buf = acc_i & 1;
         const uint32_t acc_phase = (acc_i >> 1) & 1;
         mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
@@ -166,12 +216,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t adesc = umma_desc_sw128(sa + k * 32, 16, 1024);
             uint64_t bdesc = umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (MMA2) umma2_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in every cluster CTA that multicasts into it) when these MMAs retire
+          if (MMA2) umma2_commit_mcast(&empty_bar[stage], kMask);
+          else if (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs when paired)
+        if (MMA2) umma2_commit_mcast(&tfull_bar[buf], kMask);
+        else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
@@ -182,10 +238,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const int half = p.BN >> 1;
     const int n_out_total = PAIR ? (p.N >> 1) : p.N;
     uint32_t acc_i = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_i) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
       const uint32_t buf = acc_i & 1;
       const uint32_t acc_phase = (acc_i >> 1) & 1;
-      TileCoord c = tile_coord(p, tile);
+      TileCoord c = tile_coord<CL>(p, tile, rank);
       long long m_out;
       bool valid;
       if (p.conv) {
@@ -311,15 +367,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      if (MMA2 && rank != 0) mbar_arrive_remote(&tempty_bar[buf], 0);  // the leader's MMA thread waits for both
+      else mbar_arrive(&tempty_bar[buf]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (MMA2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -366,6 +425,8 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.BN = a->bn;
   p.tiles_n = (a->N + a->bn - 1) / a->bn;
   p.conv = a->conv ? 1 : 0;
+  int cl = 1;         // cluster size along M; decided below once tiles_m is known
+  bool mma2 = false;  // cta_group::2 CTA pairs
   CUresult cr;
   if (a->conv) {
     IIR_REQUIRE(a->conv == 3 && a->stride == 1 && a->up2 == 0,
@@ -405,9 +466,30 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     return IIR_ERR_CUDA;
   }
   {
+    static int cl_env = -1;
+    if (cl_env < 0) {
+      const char* e = getenv("IIR_GEMM_CLUSTER");
+      cl_env = e ? atoi(e) : 0;  // 0 = automatic
+    }
+    // IIR_GEMM_CLUSTER: 0/unset = automatic (CTA pairs with cta_group::2 when there are >= 2 M tiles),
+    // 1 = single CTA, 2/4 = cluster multicast with cta_group::1 MMAs, 22 = force CTA pairs
+    if (cl_env == 1 || cl_env == 2 || cl_env == 4) cl = cl_env;
+    else if (cl_env == 22 || a->cluster == 2) { cl = p.tiles_m >= 2 ? 2 : 1; mma2 = cl == 2; }
+    else if (a->cluster == 1) cl = 1;
+    else {
+      // CTA pairs pay two cluster syncs (~1-2 us): worth it once the main loop is long enough to be
+      // shared-memory-bandwidth bound (measured: wins for N >= 2560 with K >= 1024 and for long-K convs)
+      const double flops = 2.0 * a->M * a->N * a->K;
+      const bool big = (a->N >= 2560 && a->K >= 1024) || (a->conv && flops >= 6e10) || flops >= 2e11;
+      cl = (big && p.tiles_m >= 2) ? 2 : 1;
+      mma2 = cl == 2;
+    }
+    while (cl > 1 && (p.tiles_m < cl || (a->bn / cl) % 8 != 0)) cl >>= 1;
+    if (cl != 2) mma2 = false;
+    p.tiles_m_cl = (p.tiles_m + cl - 1) / cl;
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * 2};
-    uint32_t box[2] = {BK, (uint32_t)a->bn};
+    uint32_t box[2] = {BK, (uint32_t)(a->bn / cl)};
     cr = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w, dims, strides, box,
                       CU_TENSOR_MAP_SWIZZLE_128B);
     if (cr != CUDA_SUCCESS) {
@@ -423,7 +505,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.out = a->out; p.out_bf16 = a->out_dtype == IIR_BF16; p.ld_out = a->ld_out;
   p.act = a->act;
 
-  const int stage_bytes = A_STAGE_BYTES + a->bn * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
@@ -431,21 +513,28 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
+  const int num_tiles = p.tiles_m_cl * p.tiles_n;  // super-tiles, one per cluster at a time
+  int grid = (sm_count() / cl) * cl;
+  if (grid > num_tiles * cl) grid = num_tiles * cl;
 
   cudaError_t e;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH(PAIRV)                                                                              \
-  e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                           (int)smem);                                                             \
-  if (e == cudaSuccess) e = launch_pdl(gemm_tc_kernel<PAIRV>, dim3(grid), dim3(GEMM_THREADS), smem, st, p);
+#define LAUNCH2(PAIRV, CLV, M2)                                                                          \
+  e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV, CLV, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)smem);                                                                    \
+  if (e == cudaSuccess)                                                                                   \
+    e = launch_cluster_pdl(gemm_tc_kernel<PAIRV, CLV, M2>, dim3(grid), dim3(GEMM_THREADS), smem, st, CLV, p);
+#define LAUNCH(PAIRV)                                \
+  if (mma2) { LAUNCH2(PAIRV, 2, true) }              \
+  else if (cl == 4) { LAUNCH2(PAIRV, 4, false) }     \
+  else if (cl == 2) { LAUNCH2(PAIRV, 2, false) }     \
+  else { LAUNCH2(PAIRV, 1, false) }
   if (a->pair == IIR_PAIR_NONE) { LAUNCH(0) }
   else if (a->pair == IIR_PAIR_GEGLU) { LAUNCH(1) }
   else if (a->pair == IIR_PAIR_SFT) { LAUNCH(2) }
   else { set_error("iir_gemm_tc: bad pair=%d", a->pair); return IIR_ERR_INVALID; }
 #undef LAUNCH
+#undef LAUNCH2
   if (e != cudaSuccess) {
     set_error("iir_gemm_tc: %s", cudaGetErrorString(e));
     return IIR_ERR_CUDA;

@@ -89,18 +89,46 @@ def choose_bn(M: int, N: int, K: int) -> int:
     for bn in range(32, 257, 32):
         tn = (N + bn - 1) // bn
         waves = (tm * tn + N_SM - 1) // N_SM
-        cyc = max(bn / 2.0, 32.0 + bn / 4.0)
+        # per 16-deep UMMA step: tensor pipe, smem operand reads (128 B/clk), L2->SM fill (~52 B/clk/SM;
+        # the weight tile is split over a 2-CTA cluster and multicast, so each CTA pulls A + B/2)
+        cyc = max(bn / 2.0, 32.0 + bn / 4.0, (4096.0 + bn * 16.0) / 52.0)
         cost = waves * ((K / 16.0) * cyc + 400.0 + 3.0 * bn)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best
 
 
+# ---- measured tile choices ------------------------------------------------------------------
+# tools/autotune.py sweeps (tile width x {one CTA, CTA pair}) for every GEMM / conv shape a step
+# launches on a B200 and writes tuning_b200.json; unseen shapes fall back to the analytic model.
+_TUNING = None
+
+
+def _tuning():
+    global _TUNING
+    if _TUNING is None:
+        import json
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning_b200.json")
+        _TUNING = {}
+        if os.path.exists(path) and os.environ.get("IIR_NO_TUNING") != "1":
+            with open(path) as f:
+                _TUNING = json.load(f).get("gemm", {})
+    return _TUNING
+
+
+def gemm_key(M, N, K, conv, pair):
+    g = f"c{conv['n_img']}x{conv['H']}x{conv['W']}" if conv is not None else "lin"
+    return f"{g}:{M}:{N}:{K}:{int(pair)}"
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
          lda: Optional[int] = None, bias=None, rowvec=None, rows_per_sample: int = 0,
          residual=None, ld_res: Optional[int] = None, aux=None, ld_aux: Optional[int] = None,
          ld_out: Optional[int] = None, act: int = ACT_NONE, pair: int = PAIR_NONE,
-         bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True):
+         bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True,
+         cluster: Optional[int] = None):
     """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1."""
     lib = _lib.load()
     n_out = N // 2 if pair else N
@@ -126,10 +154,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.out, g.out_dtype = _p(out), _dt(out)
     g.ld_out = ld_out if ld_out is not None else n_out
     g.act, g.pair = act, pair
-    g.bn = bn if bn is not None else (default_bn(N, True) if pair else choose_bn(M, N, K))
+    tuned = _tuning().get(gemm_key(M, N, K, conv, pair)) if (tc and (bn is None or cluster is None)) else None
+    if bn is None:
+        bn = default_bn(N, True) if pair else (tuned["bn"] if tuned else choose_bn(M, N, K))
+    if cluster is None:
+        cluster = tuned["cluster"] if tuned else 0
+    g.bn, g.cluster = bn, cluster
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
-    with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K):
+    with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=gemm_key(M, N, K, conv, pair),
+               conv=None if conv is None else (conv["n_img"], conv["H"], conv["W"], conv["Cin"])):
         _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt")
     return out
 

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _lib.load()
     for name in _header_symbols():
         assert hasattr(lib, name), name
-    assert lib.iir_abi_version() == 1
+    assert lib.iir_abi_version() == 2
     assert isinstance(lib.iir_launch_count(), int)
     assert lib.iir_groupnorm_scratch_floats(2, 32) == 2 * 256 * 32 * 2 + 2 * 32 * 2
 
@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
 
     fields_g = ["a", "M", "lda", "conv", "bias", "rows_per_sample", "residual", "ld_res", "aux", "out",
-                "ld_out", "act", "bn"]
+                "ld_out", "act", "bn", "cluster"]
     fields_a = ["q", "n_seg", "k", "ldk", "k_off", "v", "kv_len", "seg_scale", "out", "dtype", "n_q",
                 "softmax_scale"]
     prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "instantir_b200.h"', "int main(void){",

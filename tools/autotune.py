@@ -1,0 +1,89 @@
+"""Autotune the tcgen05 GEMM / implicit-conv tile choice on this GPU.
+
+Runs one eager step of the chosen workloads with the profiling hook to collect every distinct
+(kind, M, N, K, conv geometry, paired) the step launches, then times each with every admissible tile
+width and both CTA modes (cold L2, median of 9) and writes instantir_b200/tuning_b200.json."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from instantir_b200 import config as pcfg, ops
+from instantir_b200.pipeline import InstantIRPipeline
+from instantir_b200.schedulers import DDPMScheduler, LCMSingleStepScheduler
+torch.set_grad_enabled(False)
+dev = "cuda:0"
+os.environ["IIR_NO_TUNING"] = "1"
+
+
+def collect(cfg, latent, B, preview):
+    unet, agg = bench.build_models(cfg, dev, "bf16", with_lora=preview)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+    devin = {k: v.to(dev) for k, v in bench.host_inputs(cfg, B, latent).items()}
+    ops.PROFILE = []
+    loop = pipe(**devin, generator=torch.Generator(device=dev).manual_seed(1), prepare_only=True, num_inference_steps=30,
+                guidance_scale=7.0, previewer_scheduler=LCMSingleStepScheduler(), preview_start=0.0 if preview else 1.0,
+                use_cuda_graph=False)
+    loop.step(0)
+    torch.cuda.synchronize()
+    shapes = {}
+    for name, work, _, _ in ops.PROFILE:
+        if name in ("gemm_tc", "conv3x3_tc"):
+            shapes[work["key"]] = (work["M"], work["N"], work["K"], work["conv"], work["pair"])
+    ops.PROFILE = None
+    del pipe, unet, agg, loop
+    torch.cuda.empty_cache()
+    return shapes
+
+
+shapes = {}
+shapes.update(collect(pcfg.sdxl(), 128, 1, False))
+shapes.update(collect(pcfg.tiny(), 32, 1, True))
+print(f"{len(shapes)} distinct shapes", flush=True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=9):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e3
+
+
+table = {}
+for key, (M, N, K, conv, pair) in sorted(shapes.items(), key=lambda kv: -kv[1][0] * kv[1][1] * kv[1][2]):
+    if conv is not None:
+        n, H, W, Ci = conv
+        a = torch.randn(n, H, W, Ci, device=dev, dtype=torch.bfloat16)
+        cd = dict(n_img=n, H=H, W=W, Cin=Ci)
+    else:
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        cd = None
+    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * K ** -0.5
+    n_out = N // 2 if pair else N
+    out = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
+    aux = torch.randn(M, n_out, device=dev) if pair == ops.PAIR_SFT else None
+    bns = [ops.default_bn(N, True)] if pair else list(range(64, 257, 32))
+    best = None
+    for bn in bns:
+        for cl in (1, 2):
+            if cl == 2 and (M + 127) // 128 < 2:
+                continue
+            t = timeit(lambda: ops.gemm(a, w, out, M=M, N=N, K=K, pair=pair, aux=aux, bn=bn, conv=cd, cluster=cl))
+            if best is None or t < best[0]:
+                best = (t, bn, cl)
+    table[key] = {"bn": best[1], "cluster": best[2], "us": round(best[0], 1),
+                  "tflops": round(2.0 * M * N * K / best[0] / 1e6, 1)}
+    print(key, table[key], flush=True)
+out_path = os.path.join(ROOT, "instantir_b200", "tuning_b200.json")
+if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+    json.dump({"gpu": torch.cuda.get_device_name(0), "gemm": table}, open(os.path.join(ROOT, "gpurun_out", "tuning_b200.json"), "w"), indent=0)
+json.dump({"gpu": torch.cuda.get_device_name(0), "gemm": table}, open(out_path, "w"), indent=0)
+print("wrote", out_path)

@@ -10,4 +10,3 @@ print('e2e',d['e2e']['value'], d['e2e']['seconds_per_image_batch']); print('roof
 for k,v in sorted(d['kernel_breakdown'].items(), key=lambda kv:-kv[1]['ms'])[:7]: print(f"{k:16s} n={v['launches']:4d} {v['ms']:7.2f} ms  {v['tflops'] or 0:7.1f} TF/s {v['gbs'] or 0:7.1f} GB/s")
 PY
 tail -3 gpurun_out/bench.err
-timeout 600 python tools/profile_step.py config2 2>&1 | grep attn_tc

@@ -33,7 +33,10 @@ typedef enum {
   IIR_ERR_UNSUPPORTED = -3  /* shape outside what the sm_100a kernel handles */
 } iir_status;
 
-typedef enum { IIR_F32 = 0, IIR_BF16 = 1 } iir_dtype;
+/* A library build supports fp32 plus exactly ONE 16-bit operand type: libinstantir_b200.so = bf16,
+ * libinstantir_b200_fp16.so (-DIIR_FP16) = IEEE fp16, the reference's own inference precision
+ * (infer.py:119).  iir_h16_dtype() tells which; the other 16-bit code is rejected with IIR_ERR_INVALID. */
+typedef enum { IIR_F32 = 0, IIR_BF16 = 1, IIR_F16 = 2 } iir_dtype;
 typedef enum { IIR_ACT_NONE = 0, IIR_ACT_SILU = 1, IIR_ACT_GELU = 2 } iir_act;
 /* paired epilogues: weight rows are packed per `bn`-wide tile as [first half | second half]
  *   GEGLU: out = (x1 + b1) * gelu_erf(x2 + b2)      reference module/min_sdxl.py:502-510
@@ -41,6 +44,7 @@ typedef enum { IIR_ACT_NONE = 0, IIR_ACT_SILU = 1, IIR_ACT_GELU = 2 } iir_act;
 typedef enum { IIR_PAIR_NONE = 0, IIR_PAIR_GEGLU = 1, IIR_PAIR_SFT = 2 } iir_pair;
 
 int iir_abi_version(void);
+int iir_h16_dtype(void);
 const char* iir_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 uint64_t iir_launch_count(void);

@@ -10,15 +10,16 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")
+LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
+LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
 
 # every symbol include/instantir_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    "iir_abi_version", "iir_last_error", "iir_launch_count",
+    "iir_abi_version", "iir_h16_dtype", "iir_last_error", "iir_launch_count",
     "iir_gemm_tc", "iir_gemm_simt", "iir_conv3x3_direct",
     "iir_attn_tc", "iir_attn_simt",
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm",
@@ -65,13 +66,14 @@ class IIRError(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
 _lock = threading.Lock()
 
 
 def _declare(lib):
     vp, i, i64, f = C.c_void_p, C.c_int, C.c_int64, C.c_float
     lib.iir_abi_version.restype = i
+    lib.iir_h16_dtype.restype = i
     lib.iir_last_error.restype = C.c_char_p
     lib.iir_launch_count.restype = C.c_uint64
     lib.iir_gemm_tc.argtypes = [C.POINTER(GemmArgs), vp]
@@ -100,34 +102,38 @@ def _declare(lib):
             fn.restype = C.c_int
 
 
-def load(build_if_missing: bool = True):
-    """Return the loaded library; raises IIRError when it cannot be loaded (no fallback)."""
-    global _lib
+def load(build_if_missing: bool = True, h16: int = BF16):
+    """Return the library whose 16-bit operand type is `h16` (BF16 or F16); raises IIRError when it
+    cannot be loaded (there is no fallback)."""
     with _lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
+        if h16 in _libs:
+            return _libs[h16]
+        path = LIB_PATH if h16 == BF16 else LIB_PATH_FP16
+        if not os.path.exists(path):
             if not build_if_missing:
-                raise IIRError(f"{LIB_PATH} not found; run `python -m instantir_b200.build`")
+                raise IIRError(f"{path} not found; run `python -m instantir_b200.build`")
             from . import build as _build
 
             _build.build()
         try:
-            lib = C.CDLL(LIB_PATH)
+            lib = C.CDLL(path)
         except OSError as e:  # pragma: no cover
-            raise IIRError(f"cannot load {LIB_PATH}: {e}") from e
+            raise IIRError(f"cannot load {path}: {e}") from e
         _declare(lib)
         if lib.iir_abi_version() != 2:
             raise IIRError(f"ABI version mismatch: library {lib.iir_abi_version()}, binding 2")
-        _lib = lib
-        return _lib
+        if lib.iir_h16_dtype() != h16:
+            raise IIRError(f"{path} was built for 16-bit dtype {lib.iir_h16_dtype()}, expected {h16}")
+        _libs[h16] = lib
+        return lib
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", lib=None):
     if rc != 0:
-        msg = load().iir_last_error().decode("utf-8", "replace")
+        msg = (lib or load()).iir_last_error().decode("utf-8", "replace")
         raise IIRError(f"{what or 'iir call'} failed ({rc}): {msg}")
 
 
 def launch_count() -> int:
-    return int(load().iir_launch_count())
+    with _lock:
+        return sum(int(lib.iir_launch_count()) for lib in _libs.values())

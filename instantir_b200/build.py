@@ -16,7 +16,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libinstantir_b200.so")
+LIB = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operand type: bf16
+LIB_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # same sources with -DIIR_FP16
 SOURCES = ["api.cu", "gemm_tc.cu", "attn_tc.cu", "simt.cu", "norm.cu", "elementwise.cu", "sched.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,8 +34,9 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the sm_100a kernels cannot be built")
 
 
-def _digest(path: str) -> str:
+def _digest(path: str, extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for p in (path, os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "instantir_b200.h")):
         with open(p, "rb") as f:
             h.update(f.read())
@@ -42,17 +44,16 @@ def _digest(path: str) -> str:
     return h.hexdigest()[:16]
 
 
-def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) -> str:
-    """Compile (if stale) and return the path of the shared library."""
+def _build_variant(lib_path: str, tag: str, defines, verbose, force, ptxas_info) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     objs, jobs = [], []
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
-        obj = os.path.join(BUILD, f"{os.path.splitext(src)[0]}.{_digest(sp)}.o")
+        obj = os.path.join(BUILD, f"{os.path.splitext(src)[0]}.{tag}.{_digest(sp, ' '.join(defines))}.o")
         objs.append(obj)
         if force or not os.path.exists(obj):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", sp, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", sp, "-o", obj]
             if ptxas_info:
                 cmd[1:1] = ["-Xptxas", "-v"]
             jobs.append((src, cmd))
@@ -66,26 +67,31 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             for src, r in ex.map(run, jobs):
                 if verbose or ptxas_info or r.returncode != 0:
-                    sys.stderr.write(f"--- nvcc {src}\n{r.stdout}{r.stderr}\n")
+                    sys.stderr.write(f"--- nvcc {src} [{tag}]\n{r.stdout}{r.stderr}\n")
                 if r.returncode != 0:
-                    raise RuntimeError(f"nvcc failed on {src}")
-    stamp = os.path.join(BUILD, "link.stamp")
+                    raise RuntimeError(f"nvcc failed on {src} [{tag}]")
+    stamp = os.path.join(BUILD, f"link.{tag}.stamp")
     want = "\n".join(objs)
     have = open(stamp).read() if os.path.exists(stamp) else ""
-    if force or jobs or not os.path.exists(LIB) or have != want:
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    if force or jobs or not os.path.exists(lib_path) or have != want:
+        cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
         with open(stamp, "w") as f:
             f.write(want)
-        # drop stale objects
         keep = set(os.path.basename(o) for o in objs)
         for fn in os.listdir(BUILD):
-            if fn.endswith(".o") and fn not in keep:
+            if fn.endswith(".o") and f".{tag}." in fn and fn not in keep:
                 os.remove(os.path.join(BUILD, fn))
-    return LIB
+    return lib_path
+
+
+def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) -> str:
+    """Compile (if stale) both library variants; returns the path of the bf16 one."""
+    _build_variant(LIB_FP16, "fp16", ["-DIIR_FP16=1"], verbose, force, False)
+    return _build_variant(LIB, "bf16", [], verbose, force, ptxas_info)
 
 
 if __name__ == "__main__":

@@ -97,5 +97,6 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, c
 }  // namespace iir
 
 extern "C" int iir_abi_version(void) { return IIR_ABI_VERSION; }
+extern "C" int iir_h16_dtype(void) { return IIR_H16; }
 extern "C" const char* iir_last_error(void) { return iir::g_err; }
 extern "C" uint64_t iir_launch_count(void) { return iir::g_launches.load(std::memory_order_relaxed); }

@@ -21,7 +21,7 @@
 namespace iir {
 namespace {
 
-typedef __nv_bfloat16 bf16;
+typedef h16 bf16;
 constexpr int ATT_THREADS = 192;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KiB: Q, K_j, V_j tiles; P_j is two of these
 
@@ -297,7 +297,7 @@ int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int B) {
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)rows * ld * 2};
   uint32_t box[3] = {64, 128, 1};
-  CUresult cr = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box,
+  CUresult cr = encode_tiled(m, IIR_H16_TMA, 3, base, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
   if (cr != CUDA_SUCCESS) {
     set_error("iir_attn_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -312,7 +312,7 @@ int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int B) {
 extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   using namespace iir;
   IIR_REQUIRE(a != nullptr, "iir_attn_tc: null args");
-  IIR_REQUIRE(a->dtype == IIR_BF16, "iir_attn_tc: bf16 only (use iir_attn_simt for fp32)");
+  IIR_REQUIRE(a->dtype == IIR_H16, "iir_attn_tc: bf16 only (use iir_attn_simt for fp32)");
   IIR_REQUIRE(a->n_seg == 1 || a->n_seg == 2, "iir_attn_tc: n_seg must be 1 or 2");
   IIR_REQUIRE(a->B > 0 && a->heads > 0 && a->n_q > 0, "iir_attn_tc: empty problem");
   IIR_REQUIRE(a->ldq % 8 == 0 && a->ldo % 8 == 0 && a->q_off % 8 == 0 && a->out_off % 8 == 0,

@@ -4,13 +4,61 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
 
 #include "../../include/instantir_b200.h"
 
+// One 16-bit operand type per library build: bf16 (libinstantir_b200.so, the north star's precision) or,
+// with -DIIR_FP16, IEEE fp16 (libinstantir_b200_fp16.so — the reference's own inference precision,
+// infer.py:119; 8x finer mantissa, same tcgen05 kind::f16 rate).
+#if defined(IIR_FP16)
+typedef __half h16;
+typedef __half2 h162;
+#define IIR_H16 IIR_F16
+#define IIR_H16_TMA CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define IIR_UMMA_FMT 0u
+#else
+typedef __nv_bfloat16 h16;
+typedef __nv_bfloat162 h162;
+#define IIR_H16 IIR_BF16
+#define IIR_H16_TMA CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define IIR_UMMA_FMT 1u
+#endif
+
 namespace iir {
+
+__host__ __device__ __forceinline__ bool dtype_ok(int d) { return d == IIR_F32 || d == IIR_H16; }
+__device__ __forceinline__ float h16_to_f(h16 v) {
+#if defined(IIR_FP16)
+  return __half2float(v);
+#else
+  return __bfloat162float(v);
+#endif
+}
+__device__ __forceinline__ h16 f_to_h16(float v) {
+#if defined(IIR_FP16)
+  return __float2half_rn(v);
+#else
+  return __float2bfloat16_rn(v);
+#endif
+}
+__device__ __forceinline__ h162 ff_to_h162(float a, float b) {
+#if defined(IIR_FP16)
+  return __floats2half2_rn(a, b);
+#else
+  return __floats2bfloat162_rn(a, b);
+#endif
+}
+__device__ __forceinline__ float2 h162_to_ff(h162 v) {
+#if defined(IIR_FP16)
+  return __half22float2(v);
+#else
+  return __bfloat1622float2(v);
+#endif
+}
 
 // ---------------------------------------------------------------------------- host side
 void set_error(const char* fmt, ...);
@@ -72,39 +120,39 @@ __device__ __forceinline__ float ld_f(const T* p);
 template <>
 __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
 template <>
-__device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat162float(*p);
+__device__ __forceinline__ float ld_f<h16>(const h16* p) {
+  return h16_to_f(*p);
 }
 template <typename T>
 __device__ __forceinline__ void st_f(T* p, float v);
 template <>
 __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
 template <>
-__device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-  *p = __float2bfloat16_rn(v);
+__device__ __forceinline__ void st_f<h16>(h16* p, float v) {
+  *p = f_to_h16(v);
 }
 
 // load 4 consecutive elements as float4 (pointer must be 4-element aligned)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+__device__ __forceinline__ float4 ld4(const h16* p) {
   uint2 u = *reinterpret_cast<const uint2*>(p);
-  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
-  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
-  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  h162 a = *reinterpret_cast<h162*>(&u.x);
+  h162 b = *reinterpret_cast<h162*>(&u.y);
+  float2 fa = h162_to_ff(a), fb = h162_to_ff(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+__device__ __forceinline__ void st4(h16* p, float4 v) {
+  h162 a = ff_to_h162(v.x, v.y);
+  h162 b = ff_to_h162(v.z, v.w);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {  // packs two h16 (name kept)
+  h162 v = ff_to_h162(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -376,7 +424,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 // a/b_format BF16 [7,10),[10,13)=1, a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29).
 __device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major,
                                                              int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+  return (1u << 4) | (IIR_UMMA_FMT << 7) | (IIR_UMMA_FMT << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -4,7 +4,7 @@
 namespace iir {
 namespace {
 
-typedef __nv_bfloat16 bf16;
+typedef h16 bf16;
 
 __device__ __forceinline__ float4 ld4_any(const void* p, int is_bf16, long long idx) {
   return is_bf16 ? ld4(reinterpret_cast<const bf16*>(p) + idx)
@@ -15,11 +15,11 @@ __device__ __forceinline__ void st4_any(void* p, int is_bf16, long long idx, flo
   else st4(reinterpret_cast<float*>(p) + idx, v);
 }
 __device__ __forceinline__ float ld1_any(const void* p, int is_bf16, long long idx) {
-  return is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p)[idx])
+  return is_bf16 ? h16_to_f(reinterpret_cast<const bf16*>(p)[idx])
                  : reinterpret_cast<const float*>(p)[idx];
 }
 __device__ __forceinline__ void st1_any(void* p, int is_bf16, long long idx, float v) {
-  if (is_bf16) reinterpret_cast<bf16*>(p)[idx] = __float2bfloat16_rn(v);
+  if (is_bf16) reinterpret_cast<bf16*>(p)[idx] = f_to_h16(v);
   else reinterpret_cast<float*>(p)[idx] = v;
 }
 
@@ -149,13 +149,15 @@ extern "C" int iir_concat_inject(const void* h, int h_dtype, int C1, const void*
   IIR_REQUIRE(h && out && C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && M > 0,
               "iir_concat_inject: bad shape C1=%d C2=%d", C1, C2);
   IIR_REQUIRE(C2 == 0 || skip, "iir_concat_inject: skip missing");
+  IIR_REQUIRE(dtype_ok(h_dtype) && dtype_ok(out_dtype) && (!skip || dtype_ok(skip_dtype)) && (!rh || dtype_ok(rh_dtype)) && (!rs || dtype_ok(rs_dtype)),
+              "iir_concat_inject: unsupported dtype for this library build");
   IIR_REQUIRE(!cond_scale || rows_per_sample > 0, "iir_concat_inject: rows_per_sample missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long work = M * ((C1 + C2) / 4);
   launch_pdl(concat_inject_kernel, dim3(grid_for(work)), dim3(256), 0, st,
-      h, (int)(h_dtype == IIR_BF16), C1, rh, (int)(rh_dtype == IIR_BF16), skip, (int)(skip_dtype == IIR_BF16), C2, rs,
-      (int)(rs_dtype == IIR_BF16), cond_scale, rows_per_sample > 0 ? rows_per_sample : 1, out,
-      (int)(out_dtype == IIR_BF16), (long long)M);
+      h, (int)(h_dtype == IIR_H16), C1, rh, (int)(rh_dtype == IIR_H16), skip, (int)(skip_dtype == IIR_H16), C2, rs,
+      (int)(rs_dtype == IIR_H16), cond_scale, rows_per_sample > 0 ? rows_per_sample : 1, out,
+      (int)(out_dtype == IIR_H16), (long long)M);
   count_launch();
   return check_launch("iir_concat_inject");
 }
@@ -165,8 +167,8 @@ extern "C" int iir_upsample2x(const void* x, int x_dtype, void* out, int out_dty
   IIR_REQUIRE(x && out && n_img > 0 && H > 0 && W > 0 && C % 4 == 0, "iir_upsample2x: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long work = 4LL * n_img * H * W * (C / 4);
-  upsample2x_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_BF16, out,
-                                                    out_dtype == IIR_BF16, n_img, H, W, C);
+  upsample2x_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_H16, out,
+                                                    out_dtype == IIR_H16, n_img, H, W, C);
   count_launch();
   return check_launch("iir_upsample2x");
 }
@@ -177,19 +179,20 @@ extern "C" int iir_im2col3x3_s2(const void* x, int x_dtype, void* out, int out_d
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long work = 9LL * n_img * Ho * Wo * (C / 4);
-  im2col3x3_s2_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_BF16, out,
-                                                      out_dtype == IIR_BF16, n_img, H, W, C, Ho, Wo);
+  im2col3x3_s2_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_H16, out,
+                                                      out_dtype == IIR_H16, n_img, H, W, C, Ho, Wo);
   count_launch();
   return check_launch("iir_im2col3x3_s2");
 }
 
 extern "C" int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
                           int64_t ld_out, int64_t rows, int cols, void* stream) {
+  IIR_REQUIRE(dtype_ok(in_dtype) && dtype_ok(out_dtype), "iir_cast2d: unsupported dtype for this library build");
   IIR_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0,
               "iir_cast2d: bad shape rows=%lld cols=%d", (long long)rows, cols);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  launch_pdl(cast2d_kernel, dim3(grid_for(rows * (cols / 4))), dim3(256), 0, st, in, (int)(in_dtype == IIR_BF16),
-             (long long)ld_in, out, (int)(out_dtype == IIR_BF16), (long long)ld_out, (long long)rows, cols);
+  launch_pdl(cast2d_kernel, dim3(grid_for(rows * (cols / 4))), dim3(256), 0, st, in, (int)(in_dtype == IIR_H16),
+             (long long)ld_in, out, (int)(out_dtype == IIR_H16), (long long)ld_out, (long long)rows, cols);
   count_launch();
   return check_launch("iir_cast2d");
 }
@@ -197,7 +200,7 @@ extern "C" int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out
 extern "C" int iir_silu(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, void* stream) {
   IIR_REQUIRE(x && out && n > 0, "iir_silu: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  silu_kernel<<<grid_for(n), 256, 0, st>>>(x, x_dtype == IIR_BF16, out, out_dtype == IIR_BF16, n);
+  silu_kernel<<<grid_for(n), 256, 0, st>>>(x, x_dtype == IIR_H16, out, out_dtype == IIR_H16, n);
   count_launch();
   return check_launch("iir_silu");
 }
@@ -206,8 +209,8 @@ extern "C" int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, v
                        int out_dtype, int64_t n, void* stream) {
   IIR_REQUIRE(a && b && out && n > 0, "iir_add: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  add_kernel<<<grid_for(n), 256, 0, st>>>(a, a_dtype == IIR_BF16, b, b_dtype == IIR_BF16, out,
-                                          out_dtype == IIR_BF16, n);
+  add_kernel<<<grid_for(n), 256, 0, st>>>(a, a_dtype == IIR_H16, b, b_dtype == IIR_H16, out,
+                                          out_dtype == IIR_H16, n);
   count_launch();
   return check_launch("iir_add");
 }
@@ -217,7 +220,7 @@ extern "C" int iir_timestep_embedding(const float* t, int n, int dim, void* out,
   IIR_REQUIRE(t && out && n > 0 && dim > 0 && dim % 2 == 0, "iir_timestep_embedding: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int work = n * dim / 2;
-  timestep_embedding_kernel<<<(work + 127) / 128, 128, 0, st>>>(t, n, dim, out, out_dtype == IIR_BF16);
+  timestep_embedding_kernel<<<(work + 127) / 128, 128, 0, st>>>(t, n, dim, out, out_dtype == IIR_H16);
   count_launch();
   return check_launch("iir_timestep_embedding");
 }

@@ -322,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
               for (int j = 0; j < 32; j += 4) {
                 if (on + j < n_out_total) {
                   float4 h = p.aux_bf16
-                      ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.aux) + m_out * p.ld_aux + on + j)
+                      ? ld4(reinterpret_cast<const h16*>(p.aux) + m_out * p.ld_aux + on + j)
                       : ld4(reinterpret_cast<const float*>(p.aux) + m_out * p.ld_aux + on + j);
                   v[j] = h.x * (v[j] + 1.0f) + g[j];
                   v[j + 1] = h.y * (v[j + 1] + 1.0f) + g[j + 1];
@@ -337,14 +337,14 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             for (int j = 0; j < 32; j += 4) {
               if (on + j < n_out_total) {
                 float4 q = p.res_bf16
-                    ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.residual) + m_out * p.ld_res + on + j)
+                    ? ld4(reinterpret_cast<const h16*>(p.residual) + m_out * p.ld_res + on + j)
                     : ld4(reinterpret_cast<const float*>(p.residual) + m_out * p.ld_res + on + j);
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
               }
             }
           }
           if (p.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_out * p.ld_out + on;
+            h16* o = reinterpret_cast<h16*>(p.out) + m_out * p.ld_out + on;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (on + j < n_out_total) {
@@ -400,7 +400,8 @@ int pow2_ceil(int v) {
 extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   using namespace iir;
   IIR_REQUIRE(a != nullptr, "iir_gemm_tc: null args");
-  IIR_REQUIRE(a->a_dtype == IIR_BF16 && a->w_dtype == IIR_BF16,
+  IIR_REQUIRE(dtype_ok(a->out_dtype) && (!a->residual || dtype_ok(a->res_dtype)) && (!a->aux || dtype_ok(a->aux_dtype)), "iir_gemm_tc: unsupported dtype for this library build (fp32 or %s only)", IIR_H16 == IIR_F16 ? "fp16" : "bf16");
+  IIR_REQUIRE(a->a_dtype == IIR_H16 && a->w_dtype == IIR_H16,
               "iir_gemm_tc: operands must be bf16 (use iir_gemm_simt for the fp32 check mode)");
   IIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "iir_gemm_tc: empty problem M=%d N=%d K=%d", a->M,
               a->N, a->K);
@@ -450,7 +451,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->W * a->Cin * 2,
                            (uint64_t)a->H * a->W * a->Cin * 2};
     uint32_t box[4] = {BK, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
-    cr = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->a, dims, strides, box,
+    cr = encode_tiled(&p.tmA, IIR_H16_TMA, 4, a->a, dims, strides, box,
                       CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
     IIR_REQUIRE(a->lda % 8 == 0 && a->lda >= a->K, "iir_gemm_tc: lda=%lld invalid", (long long)a->lda);
@@ -458,7 +459,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->lda * 2};
     uint32_t box[2] = {BK, BM};
-    cr = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, dims, strides, box,
+    cr = encode_tiled(&p.tmA, IIR_H16_TMA, 2, a->a, dims, strides, box,
                       CU_TENSOR_MAP_SWIZZLE_128B);
   }
   if (cr != CUDA_SUCCESS) {
@@ -490,7 +491,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * 2};
     uint32_t box[2] = {BK, (uint32_t)(a->bn / cl)};
-    cr = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w, dims, strides, box,
+    cr = encode_tiled(&p.tmB, IIR_H16_TMA, 2, a->w, dims, strides, box,
                       CU_TENSOR_MAP_SWIZZLE_128B);
     if (cr != CUDA_SUCCESS) {
       set_error("iir_gemm_tc: cuTensorMapEncodeTiled(W) failed (%d)", (int)cr);
@@ -500,9 +501,9 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.bias = a->bias;
   p.rowvec = a->rowvec;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
-  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_BF16; p.ld_res = a->ld_res;
-  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_BF16; p.ld_aux = a->ld_aux;
-  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_BF16; p.ld_out = a->ld_out;
+  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_H16; p.ld_res = a->ld_res;
+  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;
+  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act;
 
   const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;

@@ -211,7 +211,7 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
 }  // namespace iir
 
 using namespace iir;
-typedef __nv_bfloat16 bf16;
+typedef h16 bf16;
 
 extern "C" int64_t iir_groupnorm_scratch_floats(int n_img, int groups) {
   // chunk partials followed by the finalised (mean, rstd) table
@@ -222,6 +222,7 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
                              void* out, int out_dtype, int n_img, int HW, int C, int groups,
                              float eps, int silu, float* partials, void* stream) {
   IIR_REQUIRE(x && out && partials, "iir_groupnorm: null pointer");
+  IIR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype), "iir_groupnorm: unsupported dtype for this library build (fp32 or %s only)", IIR_H16 == IIR_F16 ? "fp16" : "bf16");
   IIR_REQUIRE(n_img > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64 && C % groups == 0 &&
                   C % 4 == 0,
               "iir_groupnorm: bad shape n=%d HW=%d C=%d G=%d", n_img, HW, C, groups);
@@ -268,8 +269,8 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
       reinterpret_cast<const TI*>(x), gamma, beta, (const float*)stats, reinterpret_cast<TO*>(out), HW, C, \
       groups, nchunks, eps, silu, rpb)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
-  else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
-  else if (x_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else if (x_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
+  else if (x_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
   else GO(bf16, bf16);
 #undef GO
   count_launch();
@@ -282,6 +283,7 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
   IIR_REQUIRE(x && out && rows > 0 && C > 0 && C % 4 == 0 && C <= LN_MAX_V * 128,
               "iir_layernorm: bad shape rows=%d C=%d (C%%4==0, C<=%d)", rows, C, LN_MAX_V * 128);
   IIR_REQUIRE(!mod || rows_per_sample > 0, "iir_layernorm: mod needs rows_per_sample");
+  IIR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype), "iir_layernorm: unsupported dtype for this library build");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int blocks = (rows + 7) / 8;
   const int nv = (C / 4 + 31) / 32;
@@ -296,8 +298,8 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
     else GO2(TI, TO, 16);              \
   } while (0)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
-  else if (x_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
-  else if (x_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else if (x_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
+  else if (x_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
   else GO(bf16, bf16);
 #undef GO
 #undef GO2

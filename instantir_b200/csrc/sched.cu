@@ -6,7 +6,7 @@
 
 namespace iir {
 namespace {
-typedef __nv_bfloat16 bf16;
+typedef h16 bf16;
 
 template <typename TE>
 __global__ void __launch_bounds__(256)

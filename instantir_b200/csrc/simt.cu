@@ -123,17 +123,17 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) 
           v = v * gelu_erf_f(g);
         } else {
           float h = p.aux_bf16
-              ? ld_f(reinterpret_cast<const __nv_bfloat16*>(p.aux) + m * p.ld_aux + on)
+              ? ld_f(reinterpret_cast<const h16*>(p.aux) + m * p.ld_aux + on)
               : ld_f(reinterpret_cast<const float*>(p.aux) + m * p.ld_aux + on);
           v = h * (v + 1.0f) + g;
         }
       }
       if (p.residual) {
         v += p.res_bf16
-            ? ld_f(reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ld_res + on)
+            ? ld_f(reinterpret_cast<const h16*>(p.residual) + m * p.ld_res + on)
             : ld_f(reinterpret_cast<const float*>(p.residual) + m * p.ld_res + on);
       }
-      if (p.out_bf16) st_f(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ld_out + on, v);
+      if (p.out_bf16) st_f(reinterpret_cast<h16*>(p.out) + m * p.ld_out + on, v);
       else st_f(reinterpret_cast<float*>(p.out) + m * p.ld_out + on, v);
     }
   }
@@ -156,12 +156,12 @@ __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 template <>
-__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+__device__ __forceinline__ void ld8<h16>(const h16* p, float (&v)[8]) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const h162* h = reinterpret_cast<const h162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
+    float2 f = h162_to_ff(h[i]);
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
@@ -433,10 +433,11 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
 }  // namespace iir
 
 using namespace iir;
-typedef __nv_bfloat16 bf16;
+typedef h16 bf16;
 
 extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
   IIR_REQUIRE(a != nullptr, "iir_gemm_simt: null args");
+  IIR_REQUIRE(dtype_ok(a->a_dtype) && dtype_ok(a->w_dtype) && dtype_ok(a->out_dtype) && (!a->residual || dtype_ok(a->res_dtype)) && (!a->aux || dtype_ok(a->aux_dtype)), "iir_gemm_simt: unsupported dtype for this library build (fp32 or %s only)", IIR_H16 == IIR_F16 ? "fp16" : "bf16");
   IIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "iir_gemm_simt: empty problem");
   IIR_REQUIRE(a->pair == IIR_PAIR_NONE || (a->bn > 0 && a->bn % 2 == 0 && a->N % a->bn == 0),
               "iir_gemm_simt: paired epilogue needs N%%bn==0");
@@ -455,14 +456,14 @@ extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
   }
   p.bias = a->bias; p.rowvec = a->rowvec;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
-  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_BF16; p.ld_res = a->ld_res;
-  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_BF16; p.ld_aux = a->ld_aux;
-  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_BF16; p.ld_out = a->ld_out;
+  p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_H16; p.ld_res = a->ld_res;
+  p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;
+  p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act; p.bn = a->bn > 0 ? a->bn : 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->a_dtype == IIR_F32 && a->w_dtype == IIR_F32) launch_gemm_simt<float, float>(p, a->pair, st);
-  else if (a->a_dtype == IIR_BF16 && a->w_dtype == IIR_BF16) launch_gemm_simt<bf16, bf16>(p, a->pair, st);
-  else if (a->a_dtype == IIR_F32 && a->w_dtype == IIR_BF16) launch_gemm_simt<float, bf16>(p, a->pair, st);
+  else if (a->a_dtype == IIR_H16 && a->w_dtype == IIR_H16) launch_gemm_simt<bf16, bf16>(p, a->pair, st);
+  else if (a->a_dtype == IIR_F32 && a->w_dtype == IIR_H16) launch_gemm_simt<float, bf16>(p, a->pair, st);
   else launch_gemm_simt<bf16, float>(p, a->pair, st);
   count_launch();
   return check_launch("iir_gemm_simt");
@@ -485,8 +486,8 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
       reinterpret_cast<const TI*>(in), w, bias, reinterpret_cast<TO*>(out), out_nchw, n_img, H, W,  \
       Cin, out_H, out_row_off)
     if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GOS(float, float);
-    else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GOS(float, bf16);
-    else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GOS(bf16, float);
+    else if (in_dtype == IIR_F32 && out_dtype == IIR_H16) GOS(float, bf16);
+    else if (in_dtype == IIR_H16 && out_dtype == IIR_F32) GOS(bf16, float);
     else GOS(bf16, bf16);
 #undef GOS
     count_launch();
@@ -508,8 +509,8 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
           Cin, Cout, out_H, out_row_off);                                                             \
   } while (0)
     if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GOC(float, float);
-    else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GOC(float, bf16);
-    else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GOC(bf16, float);
+    else if (in_dtype == IIR_F32 && out_dtype == IIR_H16) GOC(float, bf16);
+    else if (in_dtype == IIR_H16 && out_dtype == IIR_F32) GOC(bf16, float);
     else GOC(bf16, bf16);
 #undef GOC
     if (e != cudaSuccess) {
@@ -526,8 +527,8 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
       reinterpret_cast<const TI*>(in), in_nchw, w, bias, reinterpret_cast<TO*>(out), out_nchw,   \
       n_img, H, W, Cin, Cout, out_H, out_row_off)
   if (in_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
-  else if (in_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
-  else if (in_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
+  else if (in_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
+  else if (in_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
   else GO(bf16, bf16);
 #undef GO
   count_launch();
@@ -536,6 +537,7 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
 
 extern "C" int iir_attn_simt(const iir_attn_args* a, void* stream) {
   IIR_REQUIRE(a != nullptr && a->n_seg >= 1 && a->n_seg <= 2, "iir_attn_simt: bad args");
+  IIR_REQUIRE(dtype_ok(a->dtype), "iir_attn_simt: unsupported dtype for this library build (fp32 or %s only)", IIR_H16 == IIR_F16 ? "fp16" : "bf16");
   AttnSimtParams p;
   memset(&p, 0, sizeof(p));
   p.q = a->q; p.ldq = a->ldq; p.q_off = a->q_off; p.n_seg = a->n_seg;
@@ -587,8 +589,8 @@ extern "C" int iir_linear_small(const void* x, int x_dtype, const void* w, int w
     else GO2(TW, TO, 16);            \
   } while (0)
   if (w_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
-  else if (w_dtype == IIR_BF16 && out_dtype == IIR_F32) GO(bf16, float);
-  else if (w_dtype == IIR_F32 && out_dtype == IIR_BF16) GO(float, bf16);
+  else if (w_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
+  else if (w_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
   else GO(bf16, bf16);
 #undef GO
 #undef GO2

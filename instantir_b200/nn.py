@@ -2,7 +2,8 @@
 module tree, hold weights pre-packed for the sm_100a kernels, and launch those kernels.
 
 Data layout: activations are NHWC / token-major ``[n_img*H*W, C]``.
-In ``bf16`` precision GEMM operands (outputs of norms, attention, GEGLU) are bf16 while the
+In ``bf16`` precision (``fp16`` is identical with IEEE-half operands: the reference's own inference
+precision, 8x finer mantissa, same tensor-core rate) GEMM operands (outputs of norms, attention, GEGLU) are bf16 while the
 *residual stream* (resnet outputs, transformer hidden states, skips) stays fp32 so that rounding
 does not accumulate over the 200+ residual adds of a forward; ``fp32`` precision is the north
 star's check mode (everything fp32, SIMT kernels).
@@ -22,14 +23,14 @@ class Runtime:
     """Execution mode shared by every layer of a model."""
 
     def __init__(self, device, precision: str = "bf16"):
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' (tcgen05 path) or 'fp32' (check mode)")
+        if precision not in ("bf16", "fp16", "fp32"):
+            raise ValueError("precision must be 'bf16' / 'fp16' (tcgen05 path) or 'fp32' (check mode)")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ops._lib.IIRError("instantir_b200 runs on CUDA only; there is no CPU fallback")
         self.precision = precision
-        self.tc = precision == "bf16"
-        self.act_dtype = torch.bfloat16 if self.tc else torch.float32
+        self.tc = precision in ("bf16", "fp16")
+        self.act_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
         self.w_dtype = self.act_dtype
         self.lora_enabled = False
 

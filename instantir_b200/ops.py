@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, BF16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, BF16, F16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
 
 
 # ---- optional per-launch profiling (bench.py's roofline leg): when PROFILE is a list every op
@@ -44,7 +44,17 @@ def _dt(t: torch.Tensor) -> int:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise TypeError(f"unsupported dtype {t.dtype} (fp32 or bf16 only)")
+    if t.dtype == torch.float16:
+        return F16
+    raise TypeError(f"unsupported dtype {t.dtype} (fp32, bf16 or fp16 only)")
+
+
+def _L(*tensors):
+    """the library build matching the 16-bit dtype of the call's tensors (bf16 build for pure-fp32 calls)"""
+    for t in tensors:
+        if t is not None and t.dtype == torch.float16:
+            return _lib.load(h16=F16)
+    return _lib.load()
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -130,7 +140,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True,
          cluster: Optional[int] = None):
     """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1."""
-    lib = _lib.load()
+    lib = _L(a, w, out)
     n_out = N // 2 if pair else N
     g = _lib.GemmArgs()
     g.a, g.w = _p(a), _p(w)
@@ -164,20 +174,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
     with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=gemm_key(M, N, K, conv, pair),
                conv=None if conv is None else (conv["n_img"], conv["H"], conv["W"], conv["Cin"])):
-        _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt")
+        _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt", lib)
     return out
 
 
 def conv3x3_direct(x, w, bias, out, *, in_nchw: bool, out_nchw: bool, n_img: int, H: int, W: int,
                    Cin: int, Cout: int, out_H: Optional[int] = None, out_row_off: int = 0):
-    lib = _lib.load()
+    lib = _L(x, out)
     _f32c(w, "w")
     _f32c(bias, "bias")
     with _Prof("conv3x3_direct", bytes=float(n_img) * H * W * (Cin * x.element_size() + Cout * out.element_size())):
         _lib.check(lib.iir_conv3x3_direct(_p(x), _dt(x), int(in_nchw), _p(w), _p(bias), _p(out), _dt(out),
                                           int(out_nchw), n_img, H, W, Cin, Cout,
                                           out_H if out_H is not None else H, out_row_off, _stream()),
-                   "iir_conv3x3_direct")
+                   "iir_conv3x3_direct", lib)
     return out
 
 
@@ -186,7 +196,7 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
               ldvs: Sequence[int], kv_lens: Sequence[int], seg_scales: Sequence[float], out,
               out_off: int, ldo: int, *, B: int, heads: int, n_q: int, softmax_scale: float,
               tc: bool = True):
-    lib = _lib.load()
+    lib = _L(q, out)
     a = _lib.AttnArgs()
     a.q, a.ldq, a.q_off = _p(q), ldq, q_off
     a.n_seg = len(ks)
@@ -201,7 +211,7 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
     a.softmax_scale = softmax_scale
     fn = lib.iir_attn_tc if tc else lib.iir_attn_simt
     with _Prof("attn_tc" if tc else "attn_simt", flops=4.0 * B * heads * n_q * sum(kv_lens) * 64, n_q=n_q, n_kv=sum(kv_lens)):
-        _lib.check(fn(C.byref(a), _stream()), "iir_attn_tc" if tc else "iir_attn_simt")
+        _lib.check(fn(C.byref(a), _stream()), "iir_attn_tc" if tc else "iir_attn_simt", lib)
     return out
 
 
@@ -214,114 +224,114 @@ def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
 
 def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int = 32,
               eps: float = 1e-5, silu: bool = False):
-    lib = _lib.load()
+    lib = _L(x, out)
     part = _gn_partials(x.device, n_img, groups)
     with _Prof("groupnorm", bytes=float(n_img) * HW * C * (2 * x.element_size() + out.element_size())):
         _lib.check(lib.iir_groupnorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
                                      _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _p(part),
-                                     _stream()), "iir_groupnorm")
+                                     _stream()), "iir_groupnorm", lib)
     return out
 
 
 def layernorm(x, gamma, beta, out, *, rows: int, C: int, eps: float = 1e-5, mod=None,
               rows_per_sample: int = 0):
-    lib = _lib.load()
+    lib = _L(x, out)
     with _Prof("layernorm", bytes=float(rows) * C * (x.element_size() + out.element_size())):
         _lib.check(lib.iir_layernorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
                                      _p(_f32c(mod, "mod")), rows_per_sample, _p(out), _dt(out), rows, C,
-                                     eps, _stream()), "iir_layernorm")
+                                     eps, _stream()), "iir_layernorm", lib)
     return out
 
 
 def concat_inject(h, C1: int, skip, C2: int, out, *, M: int, rh=None, rs=None, cond_scale=None,
                   rows_per_sample: int = 0):
-    lib = _lib.load()
+    lib = _L(h, skip, rh, rs, out)
     with _Prof("concat_inject", bytes=float(M) * (C1 + C2) * (h.element_size() + out.element_size())):
         _lib.check(lib.iir_concat_inject(_p(h), _dt(h), C1, _p(rh), _dt(rh) if rh is not None else 0,
                                          _p(skip), _dt(skip) if skip is not None else 0, C2, _p(rs),
                                          _dt(rs) if rs is not None else 0, _p(_f32c(cond_scale, "cond_scale")),
                                          rows_per_sample, _p(out), _dt(out), M, _stream()),
-                   "iir_concat_inject")
+                   "iir_concat_inject", lib)
     return out
 
 
 def upsample2x(x, out, *, n_img: int, H: int, W: int, C: int):
-    lib = _lib.load()
+    lib = _L(x, out)
     with _Prof("upsample2x", bytes=float(n_img) * H * W * C * (x.element_size() + 4 * out.element_size())):
         _lib.check(lib.iir_upsample2x(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
-                   "iir_upsample2x")
+                   "iir_upsample2x", lib)
     return out
 
 
 def im2col3x3_s2(x, out, *, n_img: int, H: int, W: int, C: int):
-    lib = _lib.load()
+    lib = _L(x, out)
     with _Prof("im2col3x3_s2", bytes=float(n_img) * H * W * C * (x.element_size() + 2.25 * out.element_size())):
         _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
-                   "iir_im2col3x3_s2")
+                   "iir_im2col3x3_s2", lib)
     return out
 
 
 def cast2d(x, ld_in: int, out, ld_out: int, *, rows: int, cols: int):
-    lib = _lib.load()
+    lib = _L(x, out)
     with _Prof("cast2d", bytes=float(rows) * cols * (x.element_size() + out.element_size())):
         _lib.check(lib.iir_cast2d(_p(x), _dt(x), ld_in, _p(out), _dt(out), ld_out, rows, cols, _stream()),
-                   "iir_cast2d")
+                   "iir_cast2d", lib)
     return out
 
 
 def silu(x, out):
-    lib = _lib.load()
-    _lib.check(lib.iir_silu(_p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream()), "iir_silu")
+    lib = _L(x, out)
+    _lib.check(lib.iir_silu(_p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream()), "iir_silu", lib)
     return out
 
 
 def add(a, b, out):
-    lib = _lib.load()
+    lib = _L(a, b, out)
     _lib.check(lib.iir_add(_p(a), _dt(a), _p(b), _dt(b), _p(out), _dt(out), out.numel(), _stream()),
-               "iir_add")
+               "iir_add", lib)
     return out
 
 
 def timestep_embedding(t, dim: int, out):
-    lib = _lib.load()
+    lib = _L(out)
     _f32c(t, "t")
     _lib.check(lib.iir_timestep_embedding(_p(t), t.numel(), dim, _p(out), _dt(out), _stream()),
-               "iir_timestep_embedding")
+               "iir_timestep_embedding", lib)
     return out
 
 
 def linear_small(x, w, bias, out, *, M: int, N: int, K: int, act: int = ACT_NONE):
-    lib = _lib.load()
+    lib = _L(w, out)
     with _Prof("linear_small", bytes=float(N) * K * w.element_size()):
         _lib.check(lib.iir_linear_small(_p(x), _dt(x), _p(w), _dt(w), _p(_f32c(bias, "bias")), _p(out),
-                                        _dt(out), M, N, K, act, _stream()), "iir_linear_small")
+                                        _dt(out), M, N, K, act, _stream()), "iir_linear_small", lib)
     return out
 
 
 def lcm_step(eps, x, out, *, alpha_prod_t: float, c_skip: float, c_out: float):
-    lib = _lib.load()
+    lib = _L(eps)
     _f32c(x, "x")
     _f32c(out, "out")
     _lib.check(lib.iir_lcm_step(_p(eps), _dt(eps), _p(x), _p(out), x.numel(), alpha_prod_t, c_skip,
-                                c_out, _stream()), "iir_lcm_step")
+                                c_out, _stream()), "iir_lcm_step", lib)
     return out
 
 
 def cfg_ddpm_step(eps_uncond, eps_cond, x, noise, prev, pred_x0, *, guidance: float,
                   alpha_prod_t: float, c_x0: float, c_xt: float, sigma: float):
-    lib = _lib.load()
+    lib = _L(eps_uncond)
     _f32c(x, "x")
     _f32c(noise, "noise")
     _f32c(prev, "prev")
     _f32c(pred_x0, "pred_x0")
     _lib.check(lib.iir_cfg_ddpm_step(_p(eps_uncond), _p(eps_cond), _dt(eps_uncond), _p(x), _p(noise),
                                      _p(prev), _p(pred_x0), x.numel(), guidance, alpha_prod_t, c_x0,
-                                     c_xt, sigma, _stream()), "iir_cfg_ddpm_step")
+                                     c_xt, sigma, _stream()), "iir_cfg_ddpm_step", lib)
     return prev
 
 
 def add_noise(x0, noise, out, *, alpha_prod_t: float):
-    lib = _lib.load()
+    lib = _L()
     _lib.check(lib.iir_add_noise(_p(_f32c(x0, "x0")), _p(_f32c(noise, "noise")), _p(_f32c(out, "out")),
-                                 x0.numel(), alpha_prod_t, _stream()), "iir_add_noise")
+                                 x0.numel(), alpha_prod_t, _stream()), "iir_add_noise", lib)
     return out

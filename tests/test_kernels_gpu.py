@@ -355,3 +355,50 @@ def test_no_cpu_fallback():
 
     with pytest.raises(IIRError):
         ops.silu(torch.zeros(8), torch.zeros(8))
+
+
+# ---------------------------------------------------------------------- fp16 library build
+def test_fp16_build_gemm_conv_attention():
+    """libinstantir_b200_fp16.so: same kernels with IEEE-half operands (8x finer mantissa than bf16)."""
+    M, N, K = 512, 320, 640
+    a = rnd(M, K, seed=1, dtype=torch.float16)
+    w = rnd(N, K, seed=2, scale=K ** -0.5, dtype=torch.float16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    ops.gemm(a, w, out, M=M, N=N, K=K)
+    torch.cuda.synchronize()
+    assert rel_l2(out, a.float() @ w.float().t()) < 6e-4
+    x = rnd(2, 16, 16, 64, seed=3, dtype=torch.float16)
+    wc = rnd(128, 9 * 64, seed=4, scale=(9 * 64) ** -0.5, dtype=torch.float16)
+    oc = torch.empty(2 * 256, 128, device=DEV)
+    ops.gemm(x, wc, oc, M=512, N=128, K=9 * 64, conv=dict(n_img=2, H=16, W=16, Cin=64))
+    torch.cuda.synchronize()
+    assert rel_l2(oc, _conv_ref(x, wc, None)) < 6e-4
+    B, heads, n = 2, 2, 256
+    C = heads * 64
+    qkv = rnd(B, n, 3 * C, seed=5, dtype=torch.float16)
+    o = torch.empty(B, n, C, device=DEV, dtype=torch.float16)
+    ops.attention(qkv, 0, 3 * C, [qkv], [C], [3 * C], [qkv], [2 * C], [3 * C], [n], [1.0], o, 0, C,
+                  B=B, heads=heads, n_q=n, softmax_scale=0.125)
+    torch.cuda.synchronize()
+    assert rel_l2(o, _sdpa_ref(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125)) < 1.5e-3
+    ln = torch.empty(64, 640, device=DEV, dtype=torch.float16)
+    xs = rnd(64, 640, seed=6)
+    ops.layernorm(xs, None, None, ln, rows=64, C=640)
+    torch.cuda.synchronize()
+    assert rel_l2(ln, F.layer_norm(xs, (640,))) < 6e-4
+
+
+def test_wrong_16bit_dtype_is_rejected_by_each_build():
+    import ctypes as C
+
+    from instantir_b200 import _lib
+
+    for h16, other in ((_lib.BF16, _lib.F16), (_lib.F16, _lib.BF16)):
+        lib = _lib.load(h16=h16)
+        assert lib.iir_h16_dtype() == h16
+        g = _lib.GemmArgs()
+        g.a_dtype = g.w_dtype = other
+        g.out_dtype = _lib.F32
+        g.M = g.N = g.K = 64
+        g.bn = 64
+        assert lib.iir_gemm_tc(C.byref(g), None) == -1

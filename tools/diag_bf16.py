@@ -27,7 +27,7 @@ for t in (958, 501, 34):
     ref_e = ounet(x, torch.tensor(t), text, added_cond_kwargs=added, cross_attention_kwargs=ck)[0]
     od, om_ = oagg(img, torch.tensor(t), text, controlnet_cond=x, added_cond_kwargs=added)
     ref_er = ounet(x, torch.tensor(t), text, added_cond_kwargs=added, cross_attention_kwargs=ck, down_block_additional_residuals=od, mid_block_additional_residual=om_)[0]
-    for prec in ("bf16", "fp32"):
+    for prec in ("bf16", "fp16", "fp32"):
         unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=alpha / oc.lora_rank), DEV, prec)
         agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, prec)
         addd = {"text_embeds": pooled.to(DEV), "time_ids": tid.to(DEV), "image_embeds": [ip[0].to(DEV)]}

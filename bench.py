@@ -233,7 +233,7 @@ def run_ours(args):
     latent = 32 if wl == "config1" else 128
     preview = wl == "config3"
     B = args.batch
-    unet, agg = build_models(cfg, dev, "bf16", with_lora=preview)
+    unet, agg = build_models(cfg, dev, args.precision, with_lora=preview)
     pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
     cfgp = parallel.CFGParallel() if (args.cfg_parallel and world > 1) else None
     host = host_inputs(cfg, B, latent, seed=1234 + (rank // 2 if cfgp else rank))
@@ -327,7 +327,10 @@ def run_ours(args):
                 ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
                 peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
                 roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
-                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 3 launches in
+                        # profiles/ncu_gemm_tc_full_r01.txt (19.1 / 31.6 / 44.7 MB): ~ operands + residual, no re-reads
+                        "traffic": 31.8e6,
                         "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                         "launches_per_step": tc["launches"], "ms_per_step": tc["ms"],
                         "flops_per_launch_avg": tc["flops"] / tc["launches"]}
@@ -339,7 +342,7 @@ def run_ours(args):
             "metric": "1024x1024 restored images per second (30 steps, CFG 7)" if wl != "config1" else "256x256 restored images per second (30-step schedule, CFG 7)",
             "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": {"config2": "BASELINE configs[1]: full SDXL UNet + InstantIR aggregator + IP-adapter, random-init, 1024² (latent 128²), 30-step DDPM schedule, CFG 7, previewer off",
                                     "config3": "BASELINE configs[2]: config 2 + LCM previewer every step (preview_start=0)",
                                     "config1": "BASELINE configs[0]: scaled-down step, 256²"}[wl],
@@ -357,6 +360,31 @@ def run_ours(args):
             "step_frac_of_sustained_peak": (step_flops * B / (ms_per_step * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)) if step_flops else None,
             "kernel_breakdown": breakdown,
         }
+        if world == 1 and args.precision == "bf16" and not args.no_fp16:
+            # the same step with IEEE-fp16 operands (the reference's own precision; meets the 1e-2 parity bar)
+            try:
+                del loop, loop2, pipe, unet, agg
+                torch.cuda.empty_cache()
+                u16, a16 = build_models(cfg, dev, "fp16", with_lora=preview)
+                p16 = InstantIRPipeline(u16, a16, DDPMScheduler())
+                l16 = p16(**devin, generator=gen, prepare_only=True, **dict(call_kw, cfg_parallel=None))
+                for i in range(args.warmup):
+                    l16.step(i % n_sched)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k16 = min(args.steps, 15)
+                f0.record()
+                for i in range(k16):
+                    l16.step((args.warmup + i) % n_sched)
+                f1.record()
+                torch.cuda.synchronize()
+                ms16 = f0.elapsed_time(f1) / k16
+                line["fp16"] = {"ms_per_step": ms16, "value": B / (STEPS_PER_IMAGE * ms16 * 1e-3), "unit": "img/s", "steps": k16,
+                                "note": "same kernels built with fp16 operands (libinstantir_b200_fp16.so)"}
+                del l16, p16, u16, a16
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                line["fp16"] = {"error": str(e)}
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -401,6 +429,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="images per rank")
     ap.add_argument("--cfg-parallel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fp16", action="store_true", help="skip the fp16 comparison leg")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="16-bit operand type of the timed run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 2
+#define IIR_ABI_VERSION 3
 
 typedef enum {
   IIR_OK = 0,
@@ -81,6 +81,8 @@ typedef struct {
   int bn;               /* N tile (multiple of 32, <=256; multiple of 64 when paired)     */
   int cluster;          /* tc: 0 = automatic, 1 = one CTA per tile, 2 = CTA pair (cta_group::2,
                            256 x bn tile, each CTA stages half of the weight tile)         */
+  int64_t ld_rowvec;    /* row stride of rowvec in floats (0 = N): lets rowvec be a column slice
+                           of the banked time-embedding projections (iir_linear_small)    */
 } iir_gemm_args;
 
 /* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */
@@ -134,8 +136,22 @@ int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* b
  * out = LN(x) * (1 + mod[b, C:2C]) + mod[b, 0:C]  (module/ip_adapter/attention_processor.py:18-26;
  * module/min_sdxl.py:534-538).                                                              */
 int iir_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta,
-                  const float* mod, int rows_per_sample, void* out, int out_dtype, int rows, int C,
-                  float eps, void* stream);
+                  const float* mod, int64_t mod_ld, int rows_per_sample, void* out, int out_dtype,
+                  int rows, int C, float eps, void* stream);   /* mod_ld: row stride of mod (0 = 2C) */
+/* Batched adaLN over many small tensors in ONE launch: the time-aware image K/V of every
+ * cross-attention layer (attention_processor.py:1173-1178) depend only on temb and on step-invariant
+ * pre-projections, so all 2 x 70 of them are produced together.  `items` is a DEVICE array;
+ * item i: out_i[r, :] = LN(x_i[r, :], eps) * (1 + mod[r / rows_per_sample, off_i + C_i : off_i + 2 C_i])
+ *                       + mod[r / rows_per_sample, off_i : off_i + C_i],  r < rows (same for all items) */
+typedef struct {
+  const float* x;       /* [rows, C] fp32 */
+  void* out;            /* [rows, C] out_dtype */
+  int64_t mod_off;      /* column offset of (shift | scale) in a row of mod */
+  int C;                /* multiple of 4, <= 2048 */
+  int pad_;
+} iir_adaln_item;
+int iir_adaln_batched(const iir_adaln_item* items, int n_items, int rows, int rows_per_sample,
+                      const float* mod, int64_t mod_ld, float eps, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data movement fused with the reference's elementwise steps

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
+ABI_VERSION = 3
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
@@ -22,7 +23,7 @@ SYMBOLS = [
     "iir_abi_version", "iir_h16_dtype", "iir_last_error", "iir_launch_count",
     "iir_gemm_tc", "iir_gemm_simt", "iir_conv3x3_direct",
     "iir_attn_tc", "iir_attn_simt",
-    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm",
+    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add",
     "iir_timestep_embedding", "iir_linear_small",
     "iir_lcm_step", "iir_cfg_ddpm_step", "iir_add_noise",
@@ -44,7 +45,12 @@ class GemmArgs(C.Structure):
         ("aux", C.c_void_p), ("aux_dtype", C.c_int), ("ld_aux", C.c_int64),
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("ld_out", C.c_int64),
         ("act", C.c_int), ("pair", C.c_int), ("bn", C.c_int), ("cluster", C.c_int),
+        ("ld_rowvec", C.c_int64),
     ]
+
+
+class AdaLNItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("mod_off", C.c_int64), ("C", C.c_int), ("pad_", C.c_int)]
 
 
 class AttnArgs(C.Structure):
@@ -84,7 +90,8 @@ def _declare(lib):
     lib.iir_groupnorm_scratch_floats.argtypes = [i, i]
     lib.iir_groupnorm_scratch_floats.restype = i64
     lib.iir_groupnorm.argtypes = [vp, i, vp, vp, vp, i, i, i, i, i, f, i, vp, vp]
-    lib.iir_layernorm.argtypes = [vp, i, vp, vp, vp, i, vp, i, i, i, f, vp]
+    lib.iir_layernorm.argtypes = [vp, i, vp, vp, vp, i64, i, vp, i, i, i, f, vp]
+    lib.iir_adaln_batched.argtypes = [vp, i, i, i, vp, i64, f, i, vp]
     lib.iir_concat_inject.argtypes = [vp, i, i, vp, i, vp, i, i, vp, i, vp, i, vp, i, i64, vp]
     lib.iir_upsample2x.argtypes = [vp, i, vp, i, i, i, i, i, vp]
     lib.iir_im2col3x3_s2.argtypes = [vp, i, vp, i, i, i, i, i, vp]
@@ -120,8 +127,8 @@ def load(build_if_missing: bool = True, h16: int = BF16):
         except OSError as e:  # pragma: no cover
             raise IIRError(f"cannot load {path}: {e}") from e
         _declare(lib)
-        if lib.iir_abi_version() != 2:
-            raise IIRError(f"ABI version mismatch: library {lib.iir_abi_version()}, binding 2")
+        if lib.iir_abi_version() != ABI_VERSION:
+            raise IIRError(f"ABI version mismatch: library {lib.iir_abi_version()}, binding {ABI_VERSION}")
         if lib.iir_h16_dtype() != h16:
             raise IIRError(f"{path} was built for 16-bit dtype {lib.iir_h16_dtype()}, expected {h16}")
         _libs[h16] = lib

@@ -101,7 +101,7 @@ class Aggregator(_EmbeddingMixin):
         if conditioning_scale != 1.0:
             raise NotImplementedError("conditioning_scale != 1 (the pipeline never passes it, pipelines/sdxl_instantir.py:1596)")
         rt, cfg = self.rt, self.cfg
-        rt._silu_cache = None
+        rt.new_forward()
         n, _, H, W = sample.shape
         emb = self._emb(sample, timestep, added_cond_kwargs)
         temb_act = silu_of(rt, emb)

@@ -200,6 +200,7 @@ class TA_IPAttnProcessor2_0:
         self.to_v_ip = Linear(rt, src, p + ".to_v_ip", bias=False)
         self.ln_k_ip = AdaLayerNorm(rt, src, p + ".ln_k_ip", hidden_size)
         self.ln_v_ip = AdaLayerNorm(rt, src, p + ".ln_v_ip", hidden_size)
+        self.batch = None  # AdaLNKVBatch once installed on a UNet (unet.set_attn_processor)
 
     def __call__(self, attn: Attention, hidden_states, encoder_hidden_states=None, attention_mask=None,
                  external_kv=None, temb=None, residual=None):
@@ -219,9 +220,13 @@ class TA_IPAttnProcessor2_0:
         nt, ni = text.shape[1], ip.shape[1]
         q = attn.to_q(attn._to_act(hidden_states), M)
         kv_t = attn.text_kv(text)
-        k_pre, v_pre = self._pre_kv(attn, ip)
-        k_i = self.ln_k_ip(k_pre, temb, rows_per_sample=ni)
-        v_i = self.ln_v_ip(v_pre, temb, rows_per_sample=ni)
+        if self.batch is not None and B <= 16:
+            # every layer's adaLN'd image K/V were produced by ONE launch at the first layer of this forward
+            k_i, v_i = self.batch.outputs(self, ip, temb)
+        else:
+            k_pre, v_pre = self._pre_kv(attn, ip)
+            k_i = self.ln_k_ip(k_pre, temb, rows_per_sample=ni)
+            v_i = self.ln_v_ip(v_pre, temb, rows_per_sample=ni)
         o = rt.empty(M, C)
         ops.attention(q, 0, C, [kv_t, k_i], [0, 0], [2 * C, C], [kv_t, v_i], [C, 0], [2 * C, C], [nt, ni],
                       [1.0, float(self.scale)], o, 0, C, B=B, heads=attn.heads, n_q=n,
@@ -238,16 +243,80 @@ def _ta_pre_kv(self, attn, ip):
     tag = "L" if rt.lora_enabled else "B"
     ip_act = []
 
-    def pre(lin):
+    def pre(lin, which):
         def make(out):
             if not ip_act:
                 ip_act.append(attn._to_act(ip))
-            if out is None:
+            if self.batch is not None and B <= 16:
+                out = self.batch.pre_buffer(self, which, tag, B * ni)   # pooled: stable address for the batched launch
+            elif out is None:
                 out = torch.empty(B * ni, C, device=rt.device, dtype=torch.float32)
             return lin(ip_act[0], B * ni, out=out)
         return make
 
-    return attn.ctx.get("ipk" + tag, ip, pre(self.to_k_ip)), attn.ctx.get("ipv" + tag, ip, pre(self.to_v_ip))
+    return attn.ctx.get("ipk" + tag, ip, pre(self.to_k_ip, 0)), attn.ctx.get("ipv" + tag, ip, pre(self.to_v_ip, 1))
+
+
+class AdaLNKVBatch:
+    """The time-aware image K/V of ALL cross-attention layers in one launch per forward.
+
+    K_i = adaLN_k(to_k_ip(img), temb), V_i = adaLN_v(to_v_ip(img), temb)
+    (module/ip_adapter/attention_processor.py:1173-1178): the projections are step-invariant (cached), the
+    modulation depends only on temb, so nothing here depends on the layer's hidden states.  The 140 adaLN
+    linears are one banked launch (nn.SmallLinearBank) and the 140 LayerNorm+modulate passes one
+    `iir_adaln_batched` launch over a device table of (pre-projection, output, mod offset, C)."""
+
+    def __init__(self, rt: Runtime, pairs):
+        self.rt = rt
+        self.procs = [p for p, _ in pairs]
+        self.attn = {id(p): a for p, a in pairs}
+        self.idx = {id(p): k for k, p in enumerate(self.procs)}
+        self.state = {}
+        self.bank = rt.adaln_bank
+        for p in self.procs:
+            self.bank.add(p.ln_k_ip.linear)
+            self.bank.add(p.ln_v_ip.linear)
+            p.batch = self
+        self.bank.listeners.append(self._invalidate)  # new modulation vectors -> every state is stale
+
+    def _invalidate(self, _out=None):
+        for st in self.state.values():
+            st["key"] = None
+
+    def _st(self, tag, rows):
+        st = self.state.get((tag, rows))
+        if st is None:
+            rt = self.rt
+            self.bank.build()
+            pre = [[torch.empty(rows, p.hidden_size, device=rt.device, dtype=torch.float32) for _ in range(2)] for p in self.procs]
+            out = [[rt.empty(rows, p.hidden_size) for _ in range(2)] for p in self.procs]
+            entries = []
+            for k, p in enumerate(self.procs):
+                entries.append((pre[k][0], out[k][0], p.ln_k_ip.linear.off, p.hidden_size))
+                entries.append((pre[k][1], out[k][1], p.ln_v_ip.linear.off, p.hidden_size))
+            nbytes = sum(rows * c * (4 + out[0][0].element_size()) for _, _, _, c in entries)
+            st = dict(pre=pre, out=out, table=ops.adaln_items(entries, rt.device), n=len(entries), key=None, bytes=float(nbytes))
+            self.state[(tag, rows)] = st
+        return st
+
+    def pre_buffer(self, proc, which, tag, rows):
+        return self._st(tag, rows)["pre"][self.idx[id(proc)]][which]
+
+    def outputs(self, proc, ip, temb):
+        rt = self.rt
+        B, ni, _ = ip.shape
+        tag = "L" if rt.lora_enabled else "B"
+        st = self._st(tag, B * ni)
+        mod = self.bank.result(silu_of(rt, temb))
+        key = _key(ip)
+        if st["key"] != key:
+            for p in self.procs:  # make sure every layer's cached pre-projection is current (dict hits when it is)
+                p._pre_kv(self.attn[id(p)], ip)
+            ops.adaln_batched(st["table"], st["n"], mod, rt.act_dtype, rows=B * ni, rows_per_sample=ni, eps=1e-6,
+                              bytes_moved=st["bytes"])
+            st["key"] = key
+        k = self.idx[id(proc)]
+        return st["out"][k][0], st["out"][k][1]
 
 
 def _ta_prefetch(self, attn, encoder_hidden_states):

@@ -57,6 +57,7 @@ struct alignas(64) GemmTcParams {
   int tiles_m_cl;  // ceil(tiles_m / CL): M super-tiles per N tile
   const float* bias;
   const float* rowvec;
+  long long ld_rowvec;
   int rows_per_sample;
   const void* residual;
   int res_bf16;
@@ -284,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
           }
           if (p.rowvec) {
-            const float* rv = p.rowvec + static_cast<long long>(sample) * p.N + pn;
+            const float* rv = p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + pn;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (pn + j < p.N) {
@@ -418,6 +419,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   IIR_REQUIRE(!a->residual || a->ld_res % 4 == 0, "iir_gemm_tc: ld_res must be a multiple of 4");
   IIR_REQUIRE(a->pair != IIR_PAIR_SFT || a->aux, "iir_gemm_tc: SFT epilogue needs aux (h)");
   IIR_REQUIRE(a->rows_per_sample > 0 || !a->rowvec, "iir_gemm_tc: rowvec needs rows_per_sample");
+  IIR_REQUIRE(!a->rowvec || (a->ld_rowvec % 4 == 0 && (reinterpret_cast<uintptr_t>(a->rowvec) & 15) == 0), "iir_gemm_tc: rowvec / ld_rowvec must be 16-byte aligned");
 
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
@@ -500,6 +502,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   }
   p.bias = a->bias;
   p.rowvec = a->rowvec;
+  p.ld_rowvec = a->ld_rowvec > 0 ? a->ld_rowvec : a->N;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
   p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_H16; p.ld_res = a->ld_res;
   p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;

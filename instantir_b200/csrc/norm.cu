@@ -140,8 +140,8 @@ constexpr int LN_MAX_V = 16;  // float4 per lane -> C <= 2048
 template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, const float* __restrict__ mod, int rows_per_sample,
-                 TO* __restrict__ out, int rows, int C, float eps) {
+                 const float* __restrict__ beta, const float* __restrict__ mod, long long mod_ld,
+                 int rows_per_sample, TO* __restrict__ out, int rows, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + warp;
   pdl_trigger();
@@ -177,7 +177,7 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   const float* shift = nullptr;
   const float* scale = nullptr;
   if (mod) {
-    const float* m = mod + (row / rows_per_sample) * 2LL * C;
+    const float* m = mod + (row / rows_per_sample) * mod_ld;
     shift = m;       // emb.chunk(2): shift first, then scale (attention_processor.py:24)
     scale = m + C;
   }
@@ -202,6 +202,64 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
         a.x = a.x * (1.f + sc.x) + sh.x; a.y = a.y * (1.f + sc.y) + sh.y;
         a.z = a.z * (1.f + sc.z) + sh.z; a.w = a.w * (1.f + sc.w) + sh.w;
       }
+      st4(orow + i * 4, a);
+    }
+  }
+}
+
+
+// ---- batched adaLN: one warp per row over n_items tensors of `rows` rows each ----------------
+template <typename TO>
+__global__ void __launch_bounds__(256)
+adaln_batched_kernel(const iir_adaln_item* __restrict__ items, int n_items, int rows,
+                     int rows_per_sample, const float* __restrict__ mod, long long mod_ld, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long grow = blockIdx.x * 8LL + warp;
+  pdl_trigger();
+  pdl_wait();
+  if (grow >= static_cast<long long>(n_items) * rows) return;
+  const int it = static_cast<int>(grow / rows);
+  const int row = static_cast<int>(grow - static_cast<long long>(it) * rows);
+  const iir_adaln_item item = items[it];
+  const int C = item.C, cv = C >> 2;
+  const float* xr = item.x + static_cast<long long>(row) * C;
+  const float* m = mod + (row / rows_per_sample) * mod_ld + item.mod_off;  // shift | scale
+  float4 v[LN_MAX_V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      v[j] = ld4(xr + i * 4);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+  const float rstd = rsqrtf(q / C + eps);
+  TO* orow = reinterpret_cast<TO*>(item.out) + static_cast<long long>(row) * C;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    int i = lane + 32 * j;
+    if (i < cv) {
+      float4 a = v[j];
+      float4 sh = ld4(m + i * 4), sc = ld4(m + C + i * 4);
+      a.x = (a.x - mean) * rstd * (1.f + sc.x) + sh.x;
+      a.y = (a.y - mean) * rstd * (1.f + sc.y) + sh.y;
+      a.z = (a.z - mean) * rstd * (1.f + sc.z) + sh.z;
+      a.w = (a.w - mean) * rstd * (1.f + sc.w) + sh.w;
       st4(orow + i * 4, a);
     }
   }
@@ -278,8 +336,11 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
 }
 
 extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta,
-                             const float* mod, int rows_per_sample, void* out, int out_dtype,
-                             int rows, int C, float eps, void* stream) {
+                             const float* mod, int64_t mod_ld_, int rows_per_sample, void* out,
+                             int out_dtype, int rows, int C, float eps, void* stream) {
+  const long long mod_ld = mod_ld_ > 0 ? mod_ld_ : 2LL * C;
+  IIR_REQUIRE(!mod || (mod_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(mod) & 15) == 0),
+              "iir_layernorm: mod / mod_ld must be 16-byte aligned");
   IIR_REQUIRE(x && out && rows > 0 && C > 0 && C % 4 == 0 && C <= LN_MAX_V * 128,
               "iir_layernorm: bad shape rows=%d C=%d (C%%4==0, C<=%d)", rows, C, LN_MAX_V * 128);
   IIR_REQUIRE(!mod || rows_per_sample > 0, "iir_layernorm: mod needs rows_per_sample");
@@ -288,7 +349,7 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
   int blocks = (rows + 7) / 8;
   const int nv = (C / 4 + 31) / 32;
 #define GO2(TI, TO, NV)                                                                                \
-  launch_pdl(layernorm_kernel<TI, TO, NV>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const TI*>(x), gamma, beta, mod, \
+  launch_pdl(layernorm_kernel<TI, TO, NV>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const TI*>(x), gamma, beta, mod, mod_ld, \
              rows_per_sample, reinterpret_cast<TO*>(out), rows, C, eps)
 #define GO(TI, TO)                     \
   do {                                 \
@@ -305,4 +366,25 @@ extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, con
 #undef GO2
   count_launch();
   return check_launch("iir_layernorm");
+}
+
+extern "C" int iir_adaln_batched(const iir_adaln_item* items, int n_items, int rows, int rows_per_sample,
+                                 const float* mod, int64_t mod_ld, float eps, int out_dtype, void* stream) {
+  IIR_REQUIRE(items && mod && n_items > 0 && rows > 0 && rows_per_sample > 0, "iir_adaln_batched: bad arguments");
+  IIR_REQUIRE(mod_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(mod) & 15) == 0,
+              "iir_adaln_batched: mod / mod_ld must be 16-byte aligned");
+  IIR_REQUIRE(dtype_ok(out_dtype), "iir_adaln_batched: unsupported dtype for this library build");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n_items) * rows;
+  const int blocks = static_cast<int>((total + 7) / 8);
+  cudaError_t e;
+  if (out_dtype == IIR_F32)
+    e = launch_pdl(adaln_batched_kernel<float>, dim3(blocks), dim3(256), 0, st, items, n_items, rows, rows_per_sample, mod,
+                   static_cast<long long>(mod_ld), eps);
+  else
+    e = launch_pdl(adaln_batched_kernel<bf16>, dim3(blocks), dim3(256), 0, st, items, n_items, rows, rows_per_sample, mod,
+                   static_cast<long long>(mod_ld), eps);
+  if (e != cudaSuccess) { set_error("iir_adaln_batched: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
+  count_launch();
+  return check_launch("iir_adaln_batched");
 }

@@ -15,6 +15,7 @@ struct GemmSimtParams {
   int conv, n_img, H, W, Cin, stride, up2, Ho, Wo;
   const float* bias;
   const float* rowvec;
+  long long ld_rowvec;
   int rows_per_sample;
   const void* residual; int res_bf16; long long ld_res;
   const void* aux; int aux_bf16; long long ld_aux;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) 
       }
       float v = acc[i][j];
       if (p.bias) v += p.bias[pn];
-      if (p.rowvec) v += p.rowvec[static_cast<long long>(sample) * p.N + pn];
+      if (p.rowvec) v += p.rowvec[static_cast<long long>(sample) * p.ld_rowvec + pn];
       if (p.act == IIR_ACT_SILU) v = silu_f(v);
       else if (p.act == IIR_ACT_GELU) v = gelu_erf_f(v);
       if (PAIR) {
@@ -454,7 +455,7 @@ extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
     IIR_REQUIRE(a->M == a->n_img * p.Ho * p.Wo, "iir_gemm_simt: conv M mismatch (M=%d, expect %d)",
                 a->M, a->n_img * p.Ho * p.Wo);
   }
-  p.bias = a->bias; p.rowvec = a->rowvec;
+  p.bias = a->bias; p.rowvec = a->rowvec; p.ld_rowvec = a->ld_rowvec > 0 ? a->ld_rowvec : a->N;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
   p.residual = a->residual; p.res_bf16 = a->res_dtype == IIR_H16; p.ld_res = a->ld_res;
   p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;

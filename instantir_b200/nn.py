@@ -33,6 +33,14 @@ class Runtime:
         self.act_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
         self.w_dtype = self.act_dtype
         self.lora_enabled = False
+        self.temb_bank = SmallLinearBank(self)    # resnet time_emb_proj (input: silu(emb))
+        self.adaln_bank = SmallLinearBank(self)   # adaLN linears of the IP-adapter processors (input: silu(temb))
+
+    def new_forward(self):
+        """start of a model forward: per-forward caches are dropped"""
+        self._silu_cache = None
+        self.temb_bank.reset()
+        self.adaln_bank.reset()
 
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.device, dtype=dtype or self.act_dtype)
@@ -130,21 +138,87 @@ class Linear:
 
 
 class SmallLinear:
-    """M <= 16 linear on fp32 vectors (time/add embeddings, time_emb_proj, adaLN)."""
+    """M <= 16 linear on fp32 vectors (time/add embeddings, time_emb_proj, adaLN).  When it belongs
+    to a SmallLinearBank, the first call of a forward with a given input computes EVERY member of the
+    bank in one launch and each member returns its column slice."""
 
-    def __init__(self, rt, src, name):
+    def __init__(self, rt, src, name, bank: "Optional[SmallLinearBank]" = None):
         self.rt = rt
         self.w = _load_w(rt, src, name)
         self.b = _bias(src, name)
         self.N, self.K = self.w.base.shape
+        self.bank, self.off = None, 0
+        if bank is not None:
+            bank.add(self)
 
     def __call__(self, x, act=ops.ACT_NONE):
         M = x.shape[0]
+        if self.bank is not None and act == ops.ACT_NONE and M <= 16:
+            return self.bank.result(x)[:, self.off:self.off + self.N]
         out = torch.empty(M, self.N, device=self.rt.device, dtype=torch.float32)
         for m0 in range(0, M, 16):
             m1 = min(M, m0 + 16)
             ops.linear_small(x[m0:m1], self.w.get(), self.b, out[m0:m1], M=m1 - m0, N=self.N, K=self.K, act=act)
         return out
+
+
+class SmallLinearBank:
+    """All small linears of a model that consume the same vector (silu(temb): 17+8 resnet
+    time_emb_proj, 140 adaLN linears) stacked along N: one HBM-bound launch per forward instead of
+    one per layer.  Members' weights become row views of the stacked tensor (no copy is kept)."""
+
+    def __init__(self, rt):
+        self.rt, self.items, self.w, self.b = rt, [], None, None
+        self.key, self.out, self.keep = None, None, None
+        self.listeners = []  # called after each recompute with (bank output)
+
+    def add(self, lin: SmallLinear):
+        assert self.w is None, "bank already built"
+        lin.bank = self
+        self.items.append(lin)
+
+    def build(self):
+        if self.w is not None or not self.items:
+            return self
+        K = self.items[0].K
+        assert all(l.K == K for l in self.items)
+        off = 0
+        for l in self.items:
+            l.off = off
+            off += l.N
+        self.N, self.K = off, K
+        dev = self.rt.device
+        base = torch.empty(off, K, device=dev, dtype=self.rt.w_dtype)
+        has_lora = any(l.w.lora is not None for l in self.items)
+        lora = torch.empty(off, K, device=dev, dtype=self.rt.w_dtype) if has_lora else None
+        bias = torch.zeros(off, device=dev, dtype=torch.float32)
+        for l in self.items:
+            sl = slice(l.off, l.off + l.N)
+            base[sl] = l.w.base
+            if lora is not None:
+                lora[sl] = l.w.lora if l.w.lora is not None else l.w.base
+            if l.b is not None:
+                bias[sl] = l.b
+            l.w = _Packed(self.rt, base[sl], None if lora is None else lora[sl])
+        self.w, self.b = _Packed(self.rt, base, lora), bias
+        return self
+
+    def reset(self):
+        self.key = None
+
+    def result(self, x):
+        if self.w is None:
+            self.build()
+        key = (x.data_ptr(), tuple(x.shape), x._version, self.rt.lora_enabled)
+        if self.key != key:
+            M = x.shape[0]
+            if self.out is None or self.out.shape[0] != M:
+                self.out = torch.empty(M, self.N, device=self.rt.device, dtype=torch.float32)
+            ops.linear_small(x, self.w.get(), self.b, self.out, M=M, N=self.N, K=self.K)
+            self.key, self.keep = key, x
+            for fn in self.listeners:
+                fn(self.out)
+        return self.out
 
 
 class Conv3x3:
@@ -220,7 +294,7 @@ class ResnetBlock2D:
         self.rt, self.c_in, self.c_out = rt, c_in, c_out
         self.norm1 = GroupNorm(rt, src, p + ".norm1", c_in, cfg.norm_num_groups, cfg.norm_eps)
         self.conv1 = Conv3x3(rt, src, p + ".conv1")
-        self.time_emb_proj = SmallLinear(rt, src, p + ".time_emb_proj")
+        self.time_emb_proj = SmallLinear(rt, src, p + ".time_emb_proj", bank=rt.temb_bank)
         self.norm2 = GroupNorm(rt, src, p + ".norm2", c_out, cfg.norm_num_groups, cfg.norm_eps)
         self.conv2 = Conv3x3(rt, src, p + ".conv2")
         self.conv_shortcut = None

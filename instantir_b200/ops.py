@@ -75,6 +75,16 @@ def _f32c(t: Optional[torch.Tensor], name: str):
     return t
 
 
+def _f32rows(t: Optional[torch.Tensor], name: str):
+    """fp32 [rows, n] tensor whose rows are contiguous (a column slice of a wider buffer is fine);
+    returns (tensor, row stride in elements; 0 when None)."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32 or t.ndim != 2 or t.stride(1) != 1:
+        raise TypeError(f"{name} must be an fp32 [rows, n] tensor with unit column stride")
+    return t, t.stride(0)
+
+
 N_SM = 148  # B200
 
 
@@ -153,7 +163,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         g.stride = conv.get("stride", 1)
         g.up2 = conv.get("up2", 0)
     g.bias = _p(_f32c(bias, "bias"))
-    g.rowvec = _p(_f32c(rowvec, "rowvec"))
+    rowvec, g.ld_rowvec = _f32rows(rowvec, "rowvec")
+    g.rowvec = _p(rowvec)
     g.rows_per_sample = rows_per_sample
     if residual is not None:
         g.residual, g.res_dtype = _p(residual), _dt(residual)
@@ -236,11 +247,34 @@ def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int =
 def layernorm(x, gamma, beta, out, *, rows: int, C: int, eps: float = 1e-5, mod=None,
               rows_per_sample: int = 0):
     lib = _L(x, out)
+    mod, mod_ld = _f32rows(mod, "mod")
     with _Prof("layernorm", bytes=float(rows) * C * (x.element_size() + out.element_size())):
         _lib.check(lib.iir_layernorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
-                                     _p(_f32c(mod, "mod")), rows_per_sample, _p(out), _dt(out), rows, C,
+                                     _p(mod), mod_ld, rows_per_sample, _p(out), _dt(out), rows, C,
                                      eps, _stream()), "iir_layernorm", lib)
     return out
+
+
+def adaln_items(entries, device) -> torch.Tensor:
+    """device table for adaln_batched: entries = [(x fp32 [rows,C], out [rows,C], mod column offset, C)]."""
+    arr = (_lib.AdaLNItem * len(entries))()
+    for k, (x, out, off, c) in enumerate(entries):
+        if x.dtype != torch.float32 or not x.is_contiguous() or not out.is_contiguous():
+            raise TypeError("adaln_items: x must be contiguous fp32, out contiguous")
+        arr[k].x, arr[k].out, arr[k].mod_off, arr[k].C = _p(x), _p(out), off, c
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return raw.to(device)
+
+
+def adaln_batched(table: torch.Tensor, n_items: int, mod, out_dtype, *, rows: int, rows_per_sample: int,
+                  eps: float = 1e-6, bytes_moved: float = 0.0):
+    """every item's LN(x)*(1+scale)+shift in one launch (table from adaln_items)."""
+    lib = _lib.load(h16=F16) if out_dtype == torch.float16 else _lib.load()
+    mod, mod_ld = _f32rows(mod, "mod")
+    dt = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}[out_dtype]
+    with _Prof("adaln_batched", bytes=bytes_moved):
+        _lib.check(lib.iir_adaln_batched(_p(table), n_items, rows, rows_per_sample, _p(mod), mod_ld, eps, dt,
+                                         _stream()), "iir_adaln_batched", lib)
 
 
 def concat_inject(h, C1: int, skip, C2: int, out, *, M: int, rh=None, rs=None, cond_scale=None,

@@ -278,8 +278,14 @@ class UNet2DConditionModel(_EmbeddingMixin):
         return {name + ".processor": a.processor for name, a in self.attention_modules()}
 
     def set_attn_processor(self, processor):
+        from .attention_processor import AdaLNKVBatch, TA_IPAttnProcessor2_0
+        from .nn import SmallLinearBank
+
         for name, a in self.attention_modules():
             a.set_processor(processor[name + ".processor"] if isinstance(processor, dict) else processor)
+        pairs = [(a.processor, a) for _, a in self.attention_modules() if isinstance(a.processor, TA_IPAttnProcessor2_0)]
+        self.rt.adaln_bank = SmallLinearBank(self.rt)
+        self.adaln_batch = AdaLNKVBatch(self.rt, pairs) if pairs and len({id(p) for p, _ in pairs}) == len(pairs) else None
 
     def enable_adapters(self):
         """previewer LoRA on (peft enable_adapters, pipelines/sdxl_instantir.py:1545): selects the
@@ -324,7 +330,7 @@ class UNet2DConditionModel(_EmbeddingMixin):
         is an extension: residuals are multiplied by it inside the fused concat kernel instead of by
         separate elementwise kernels (pipelines/sdxl_instantir.py:1602-1603)."""
         rt, cfg = self.rt, self.cfg
-        rt._silu_cache = None
+        rt.new_forward()
         n, _, H, W = sample.shape
         kw = dict(cross_attention_kwargs or {})
         emb = self._emb(sample, timestep, added_cond_kwargs)

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _lib.load()
     for name in _header_symbols():
         assert hasattr(lib, name), name
-    assert lib.iir_abi_version() == 2
+    assert lib.iir_abi_version() == _lib.ABI_VERSION
     assert isinstance(lib.iir_launch_count(), int)
     assert lib.iir_groupnorm_scratch_floats(2, 32) == 2 * 256 * 32 * 2 + 2 * 32 * 2
 
@@ -33,11 +33,12 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
 
     fields_g = ["a", "M", "lda", "conv", "bias", "rows_per_sample", "residual", "ld_res", "aux", "out",
-                "ld_out", "act", "bn", "cluster"]
+                "ld_out", "act", "bn", "cluster", "ld_rowvec"]
     fields_a = ["q", "n_seg", "k", "ldk", "k_off", "v", "kv_len", "seg_scale", "out", "dtype", "n_q",
                 "softmax_scale"]
     prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "instantir_b200.h"', "int main(void){",
-            'printf("%zu %zu\\n", sizeof(iir_gemm_args), sizeof(iir_attn_args));']
+            'printf("%zu %zu\\n", sizeof(iir_gemm_args), sizeof(iir_attn_args));',
+            'printf("%zu %zu %zu\\n", sizeof(iir_adaln_item), offsetof(iir_adaln_item, mod_off), offsetof(iir_adaln_item, C));']
     prog += [f'printf("%zu\\n", offsetof(iir_gemm_args, {f}));' for f in fields_g]
     prog += [f'printf("%zu\\n", offsetof(iir_attn_args, {f}));' for f in fields_a]
     prog += ["return 0;}"]
@@ -48,6 +49,8 @@ def test_struct_layout_matches_header(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     nums = [int(x) for x in out]
     assert nums[0] == ctypes.sizeof(_lib.GemmArgs) and nums[1] == ctypes.sizeof(_lib.AttnArgs)
+    assert nums[2:5] == [ctypes.sizeof(_lib.AdaLNItem), _lib.AdaLNItem.mod_off.offset, _lib.AdaLNItem.C.offset]
+    nums = nums[:2] + nums[5:]
     got = [getattr(_lib.GemmArgs, f).offset for f in fields_g] + [getattr(_lib.AttnArgs, f).offset for f in fields_a]
     assert nums[2:] == got
 

@@ -268,6 +268,43 @@ def test_layernorm_affine_and_adaln(C):
     assert rel_l2(out, ref) < 2e-5
 
 
+def test_adaln_batched_and_strided_mod():
+    """one launch over several tensors of different width == per-tensor adaLN; mod is a column slice"""
+    rows, rps, Cs = 64, 32, [128, 256, 128]
+    total = sum(2 * c for c in Cs) + 64
+    mod_all = rnd(rows // rps, total, seed=9) * 0.3
+    xs = [rnd(rows, c, seed=10 + k) * 2 + 0.5 for k, c in enumerate(Cs)]
+    outs = [torch.empty(rows, c, device=DEV, dtype=torch.bfloat16) for c in Cs]
+    offs, o = [], 64
+    for c in Cs:
+        offs.append(o)
+        o += 2 * c
+    table = ops.adaln_items([(x, out, off, c) for x, out, off, c in zip(xs, outs, offs, Cs)], DEV)
+    ops.adaln_batched(table, len(Cs), mod_all, torch.bfloat16, rows=rows, rows_per_sample=rps, eps=1e-6)
+    torch.cuda.synchronize()
+    for x, out, off, c in zip(xs, outs, offs, Cs):
+        m = mod_all[:, off:off + 2 * c].repeat_interleave(rps, 0)
+        ref = F.layer_norm(x, (c,), None, None, 1e-6) * (1 + m[:, c:]) + m[:, :c]
+        assert rel_l2(out, ref) < 4e-3
+        single = torch.empty(rows, c, device=DEV)
+        ops.layernorm(x, None, None, single, rows=rows, C=c, eps=1e-6, mod=mod_all[:, off:off + 2 * c], rows_per_sample=rps)
+        torch.cuda.synchronize()
+        assert rel_l2(single, ref) < 2e-5
+
+
+def test_gemm_rowvec_column_slice():
+    """rowvec taken as a column slice of a wider buffer (banked time_emb_proj outputs)"""
+    M, N, K, rps = 256, 128, 64, 128
+    a, w = rnd(M, K, seed=1, dtype=torch.bfloat16), rnd(N, K, seed=2, dtype=torch.bfloat16)
+    wide = rnd(M // rps, 3 * N, seed=3)
+    for tc in (True, False):
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm(a, w, out, M=M, N=N, K=K, rowvec=wide[:, N:2 * N], rows_per_sample=rps, tc=tc)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().t() + wide[:, N:2 * N].repeat_interleave(rps, 0)
+        assert rel_l2(out, ref) < 1e-5
+
+
 # ----------------------------------------------------------------------- movement / small
 def test_concat_inject_and_plain_add():
     M, C1, C2, rps = 512, 128, 64, 256

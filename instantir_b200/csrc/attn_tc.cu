@@ -16,6 +16,8 @@
 //                128B-swizzled smem (A operand of the PV MMA).
 // Two segments = decoupled text + image cross-attention with independent softmaxes
 // (module/ip_adapter/attention_processor.py:1165-1192); one segment = self-attention (:394-396).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace iir {
@@ -293,6 +295,278 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   }
 }
 
+// ==================================================================================================
+// One-segment (self-attention) kernel, second generation: P never touches shared memory.
+//
+//   TMEM (256 columns per CTA, two CTAs per SM):  S fp32 [0,128) | P 16-bit packed [128,192) | O fp32 [192,256)
+//   warps 0..3 : softmax warpgroup, one query row per thread (TMEM lane == row), 216 registers each
+//                (setmaxnreg) so the whole 128-column S row lives in registers without spills
+//   warp 4     : TMA producer — Q once, then (K_j, V_j) 128-key blocks in a 3-deep ring
+//   warp 5     : single-thread MMA issuer — S_j = Q K_jᵀ (SS: both operands in smem, 128x128x16 x4),
+//                O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major in smem, 128x64x16 x8)
+//   warps 6..7 : idle (complete the second warpgroup, 40 registers)
+// Versus the first generation (P through 128B-swizzled smem): no 32 KiB P write + 32 KiB P read per block
+// on the 128 B/clk shared-memory port (it was ~90 % busy with two CTAs per SM), one more K/V stage in the
+// freed space, and no local-memory spills in the exp loop.
+constexpr int ATS_THREADS = 256;
+constexpr int ATS_KV_STAGES = 3;
+
+__global__ void __launch_bounds__(ATS_THREADS, 2)
+attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;                      // ATS_KV_STAGES tiles
+  uint8_t* sV = sK + ATS_KV_STAGES * TILE_BYTES;      // ATS_KV_STAGES tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATS_KV_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;                             // 1
+  uint64_t* kv_full = bars + 1;                        // ATS_KV_STAGES
+  uint64_t* kv_empty = kv_full + ATS_KV_STAGES;        // ATS_KV_STAGES
+  uint64_t* s_full = kv_empty + ATS_KV_STAGES;         // 1
+  uint64_t* s_empty = s_full + 1;                      // 1
+  uint64_t* p_full = s_empty + 1;                      // 2: P columns [0,32) / [32,64) written
+  uint64_t* p_empty = p_full + 2;                      // 2: the MMAs reading that half of P retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nb = p.nblk[0];
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK[0]);
+    tma_prefetch_desc(&p.tmV[0]);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    for (int hh = 0; hh < 2; ++hh) {
+      mbar_init(&p_full[hh], 128);
+      mbar_init(&p_empty[hh], 1);
+    }
+    for (int s = 0; s < ATS_KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 128 columns fp32
+  const uint32_t tmem_P = tmem_base + 128;  // 64 columns: 128 probabilities, two per column
+  const uint32_t tmem_O = tmem_base + 192;  // 64 columns fp32, accumulated across key blocks
+
+  if (warp >= 4) {
+    setmaxnreg_dec<40>();
+    pdl_wait();
+    if (warp == 4 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int jb = 0; jb < nb; ++jb) {
+        mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
+        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_3d(sK + st * TILE_BYTES, &p.tmK[0], &kv_full[st], p.k_off[0] + h * 64, jb * 128, b);
+        tma_load_3d(sV + st * TILE_BYTES, &p.tmV[0], &kv_full[st], p.v_off[0] + h * 64, jb * 128, b);
+        if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
+      }
+    } else if (warp == 5 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // A (=P) K-major in TMEM, B (=V) MN-major
+      // O += P_j V_j in two halves of 64 keys: the first half's MMAs run under the exps of the second
+      auto issue_pv = [&](int j, int st) {
+        const uint32_t va = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait_sleep(&p_full[hh], j & 1, 2000);
+          tc_fence_after();
+#pragma unroll
+          for (int k = hh * 4; k < hh * 4 + 4; ++k) {
+            uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
+            umma_ts_bf16(tmem_O, tmem_P + k * 8, bdesc, idesc_pv, (k != 0 || j != 0) ? 1u : 0u);
+          }
+          if (hh == 1) umma_commit(&kv_empty[st]);
+          umma_commit(&p_empty[hh]);  // this half of P is free; after hh == 1, O is stable
+        }
+      };
+      mbar_wait(q_full, 0);
+      const uint32_t qa = smem_u32(sQ);
+      int st = 0, st_prev = 0;
+      uint32_t ph = 0;
+      for (int jb = 0; jb < nb; ++jb) {
+        mbar_wait_sleep(&kv_full[st], ph, 2000);
+        mbar_wait_sleep(s_empty, (jb & 1) ^ 1, 2000);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t adesc = umma_desc_sw128(qa + k * 32, 16, 1024);
+          uint64_t bdesc = umma_desc_sw128(ka + k * 32, 16, 1024);
+          umma_bf16(tmem_S, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (jb > 0) issue_pv(jb - 1, st_prev);
+        st_prev = st;
+        if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
+      }
+      issue_pv(nb - 1, st_prev);
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warpgroup
+    setmaxnreg_inc<216>();
+    pdl_wait();
+    const int lane_base = warp * 32;
+    const int row = lane_base + lane;
+    const uint32_t trow = static_cast<uint32_t>(lane_base) << 16;
+    const float sl2 = p.scale_log2;
+    const float kLazy = 8.0f / sl2;  // advance the reference max only when exp2 arguments would exceed 8
+    const int qi = q0 + row;
+    bf16* optr = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
+    float m_ref = -INFINITY, l_run = 0.f;
+#pragma unroll 1
+    for (int jb = 0; jb < nb; ++jb) {
+      const int valid = min(128, p.kv_len[0] - jb * 128);
+      mbar_wait(s_full, jb & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+      {
+        uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[0]);
+        uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[32]);
+        uint32_t (&a2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[64]);
+        uint32_t (&a3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sr[96]);
+        tmem_ld32(tmem_S + trow, a0);
+        tmem_ld32(tmem_S + trow + 32, a1);
+        tmem_ld32(tmem_S + trow + 64, a2);
+        tmem_ld32(tmem_S + trow + 96, a3);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty);  // S is in registers: Q K_{j+1}^T may overwrite the TMEM buffer now
+      if (valid < 128) {
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
+          if (j >= valid) sr[j] = 0xff800000u;  // -inf
+      }
+      float mxs[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxs[c] = __uint_as_float(sr[c]);
+#pragma unroll
+      for (int j = 8; j < 128; j += 8)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(sr[j + c]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      const bool first = (jb == 0);
+      const bool grow = !first && (mx > m_ref + kLazy);
+      const float m_old = m_ref;
+      if (first || grow) m_ref = mx;
+      const float mneg = -m_ref * sl2;
+      float sums[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sums[c] = 0.f;
+      // exps of the first 64 keys are computed BEFORE waiting for P V_{j-1}: its tail is hidden under them
+      uint32_t pk0[16], pk1[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(sr[j]), sl2, mneg));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), sl2, mneg));
+        sums[j & 7] += e0;
+        sums[(j + 1) & 7] += e1;
+        pk0[j >> 1] = pack_bf16(e0, e1);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(sr[32 + j]), sl2, mneg));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(sr[32 + j + 1]), sl2, mneg));
+        sums[j & 7] += e0;
+        sums[(j + 1) & 7] += e1;
+        pk1[j >> 1] = pack_bf16(e0, e1);
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        // rare: rescale O (TMEM) and l by exp2((m_old - mx) * sl2) for the rows that need it; O must be stable
+        mbar_wait(&p_empty[1], (jb & 1) ^ 1);
+        tc_fence_after();
+        const float alpha = grow ? ex2_approx((m_old - mx) * sl2) : 1.0f;
+        l_run *= alpha;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(tmem_O + trow + half * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 32; ++d) r[d] = __float_as_uint(__uint_as_float(r[d]) * alpha);
+          tmem_st32(tmem_O + trow + half * 32, r);
+        }
+        tmem_st_wait();
+      }
+      mbar_wait(&p_empty[0], (jb & 1) ^ 1);  // first half of P V_{j-1} retired: P columns [0,32) are free
+      tc_fence_after();
+      tmem_st16(tmem_P + trow, pk0);
+      tmem_st16(tmem_P + trow + 16, pk1);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[0]);
+#pragma unroll
+      for (int g = 2; g < 4; ++g) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[g * 32 + j]), sl2, mneg));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[g * 32 + j + 1]), sl2, mneg));
+          sums[j & 7] += e0;
+          sums[(j + 1) & 7] += e1;
+          pk[j >> 1] = pack_bf16(e0, e1);
+        }
+        if (g == 2) {
+          mbar_wait(&p_empty[1], (jb & 1) ^ 1);  // all of P V_{j-1} retired
+          tc_fence_after();
+        }
+        tmem_st16(tmem_P + trow + g * 16, pk);
+      }
+      l_run += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[1]);
+    }
+    // all key blocks done: wait for the last P V, then O / l
+    mbar_wait(&p_empty[1], (nb - 1) & 1);
+    tc_fence_after();
+    const float w = p.seg_scale[0] / l_run;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(tmem_O + trow + half * 32, r);
+      tmem_ld_wait();
+      if (qi < p.n_q) {
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[d]) * w, __uint_as_float(r[d + 1]) * w);
+          u.y = pack_bf16(__uint_as_float(r[d + 2]) * w, __uint_as_float(r[d + 3]) * w);
+          u.z = pack_bf16(__uint_as_float(r[d + 4]) * w, __uint_as_float(r[d + 5]) * w);
+          u.w = pack_bf16(__uint_as_float(r[d + 6]) * w, __uint_as_float(r[d + 7]) * w);
+          *reinterpret_cast<uint4*>(optr + half * 32 + d) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
 int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int B) {
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)rows * ld * 2};
@@ -347,7 +621,15 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   dim3 grid((a->n_q + 127) / 128, a->heads, a->B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (a->n_seg == 1) {
+  static int v1 = -1;
+  if (v1 < 0) {
+    const char* ev = getenv("IIR_ATTN_V1");
+    v1 = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  if (a->n_seg == 1 && !v1) {
+    e = cudaFuncSetAttribute(attn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel, grid, dim3(ATS_THREADS), smem, st, p);
+  } else if (a->n_seg == 1) {
     e = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = launch_pdl(attn_tc_kernel<1>, grid, dim3(ATT_THREADS), smem, st, p);
   } else {

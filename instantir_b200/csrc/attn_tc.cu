@@ -94,64 +94,68 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const uint32_t tmem_O = tmem_base + 128;  // 64 columns, accumulated across key blocks
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- TMA producer (whole warp, elected issue)
+    if (elect_one()) {
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
-      int jb = 0;
-      for (int s = 0; s < NSEG; ++s) {
-        for (int jl = 0; jl < p.nblk[s]; ++jl, ++jb) {
-          const int st = jb & 1;
-          const uint32_t ph = (jb >> 1) & 1;
-          mbar_wait(&kv_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    int jb = 0;
+    for (int s = 0; s < NSEG; ++s) {
+      for (int jl = 0; jl < p.nblk[s]; ++jl, ++jb) {
+        const int st = jb & 1;
+        const uint32_t ph = (jb >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
           tma_load_3d(sK + st * TILE_BYTES, &p.tmK[s], &kv_full[st], p.k_off[s] + h * 64, jl * 128, b);
           tma_load_3d(sV + st * TILE_BYTES, &p.tmV[s], &kv_full[st], p.v_off[s] + h * 64, jl * 128, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
-      const int seg1_first = p.nblk[0];  // first flat block index of the second segment
-      auto issue_pv = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP);
-        const uint32_t va = smem_u32(sV + st * TILE_BYTES);
-        const bool fresh = (j == 0) || (NSEG > 1 && j == seg1_first);  // first block of a segment
+    // ---------------------------------------------------------------- MMA issuer (whole warp, elected issue)
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+    const int seg1_first = p.nblk[0];  // first flat block index of the second segment
+    auto issue_pv = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP);
+      const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV + st * TILE_BYTES), 1024, 1024);
+      const bool fresh = (j == 0) || (NSEG > 1 && j == seg1_first);  // first block of a segment
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t adesc = umma_desc_sw128(pa + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
-          uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
-          umma_bf16(tmem_O, adesc, bdesc, idesc_pv, (k != 0 || !fresh) ? 1u : 0u);
+          umma_bf16(tmem_O, adesc, vdesc0 + 128 * k, idesc_pv, (k != 0 || !fresh) ? 1u : 0u);
         }
         umma_commit(&kv_empty[st]);
         umma_commit(p_empty);  // PV_j retired: P buffer free and O stable
-      };
-      mbar_wait(q_full, 0);
-      const uint32_t qa = smem_u32(sQ);
-      for (int jb = 0; jb < nb_total; ++jb) {
-        const int st = jb & 1;
-        const uint32_t ph = (jb >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
-        mbar_wait(s_empty, (jb & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t ka = smem_u32(sK + st * TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t adesc = umma_desc_sw128(qa + k * 32, 16, 1024);
-          uint64_t bdesc = umma_desc_sw128(ka + k * 32, 16, 1024);
-          umma_bf16(tmem_S, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
-        }
-        umma_commit(s_full);
-        if (jb > 0) issue_pv(jb - 1);
       }
-      issue_pv(nb_total - 1);
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    for (int jb = 0; jb < nb_total; ++jb) {
+      const int st = jb & 1;
+      const uint32_t ph = (jb >> 1) & 1;
+      mbar_wait(&kv_full[st], ph);
+      mbar_wait(s_empty, (jb & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_S, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      if (jb > 0) issue_pv(jb - 1);
     }
+    issue_pv(nb_total - 1);
   } else {
     // ---------------------------------------------------------------- softmax warps
     const int lane_base = (warp & 3) * 32;
@@ -362,55 +366,64 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
   if (warp >= 4) {
     setmaxnreg_dec<40>();
     pdl_wait();
-    if (warp == 4 && lane == 0) {
+    // Both single-issuer roles run their loops with the WHOLE warp (warp-uniform control flow keeps
+    // descriptors / coordinates in uniform registers) and elect one lane per instruction group.
+    if (warp == 4) {
       // ---------------------------------------------------------------- TMA producer
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
+      }
+      __syncwarp();
       int st = 0;
       uint32_t ph = 0;
       for (int jb = 0; jb < nb; ++jb) {
         mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
-        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        tma_load_3d(sK + st * TILE_BYTES, &p.tmK[0], &kv_full[st], p.k_off[0] + h * 64, jb * 128, b);
-        tma_load_3d(sV + st * TILE_BYTES, &p.tmV[0], &kv_full[st], p.v_off[0] + h * 64, jb * 128, b);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          tma_load_3d(sK + st * TILE_BYTES, &p.tmK[0], &kv_full[st], p.k_off[0] + h * 64, jb * 128, b);
+          tma_load_3d(sV + st * TILE_BYTES, &p.tmV[0], &kv_full[st], p.v_off[0] + h * 64, jb * 128, b);
+        }
+        __syncwarp();
         if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
       }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == 5) {
       // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // A (=P) K-major in TMEM, B (=V) MN-major
       // O += P_j V_j in two halves of 64 keys: the first half's MMAs run under the exps of the second
       auto issue_pv = [&](int j, int st) {
-        const uint32_t va = smem_u32(sV + st * TILE_BYTES);
+        const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV + st * TILE_BYTES), 1024, 1024);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           mbar_wait_sleep(&p_full[hh], j & 1, 2000);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = hh * 4; k < hh * 4 + 4; ++k) {
-            uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
-            umma_ts_bf16(tmem_O, tmem_P + k * 8, bdesc, idesc_pv, (k != 0 || j != 0) ? 1u : 0u);
+            for (int k = hh * 4; k < hh * 4 + 4; ++k)  // +16 keys = +2048 B = +128 in the (addr >> 4) field
+              umma_ts_bf16(tmem_O, tmem_P + k * 8, vdesc0 + 128 * k, idesc_pv, (k != 0 || j != 0) ? 1u : 0u);
+            if (hh == 1) umma_commit(&kv_empty[st]);
+            umma_commit(&p_empty[hh]);  // this half of P is free; after hh == 1, O is stable
           }
-          if (hh == 1) umma_commit(&kv_empty[st]);
-          umma_commit(&p_empty[hh]);  // this half of P is free; after hh == 1, O is stable
+          __syncwarp();
         }
       };
       mbar_wait(q_full, 0);
-      const uint32_t qa = smem_u32(sQ);
+      const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
       int st = 0, st_prev = 0;
       uint32_t ph = 0;
       for (int jb = 0; jb < nb; ++jb) {
         mbar_wait_sleep(&kv_full[st], ph, 2000);
         mbar_wait_sleep(s_empty, (jb & 1) ^ 1, 2000);
         tc_fence_after();
-        const uint32_t ka = smem_u32(sK + st * TILE_BYTES);
+        const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t adesc = umma_desc_sw128(qa + k * 32, 16, 1024);
-          uint64_t bdesc = umma_desc_sw128(ka + k * 32, 16, 1024);
-          umma_bf16(tmem_S, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_S, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
         if (jb > 0) issue_pv(jb - 1, st_prev);
         st_prev = st;
         if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }

@@ -150,7 +150,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps coordinates and descriptors in
+    // uniform registers: no per-instruction R2UR "waterfall"); one elected lane issues the copies.
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int cpb = p.conv ? p.Cin / BK : 1;  // 64-channel blocks per filter tap
@@ -161,43 +163,40 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (MMA2) {
-            // both CTAs' loads complete_tx on the leader's barrier: it expects 2 x stage_bytes
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
-            if (p.conv) {
-              int tap = kb / cpb;
-              int cb = kb - tap * cpb;
-              int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d_2sm(sa, &p.tmA, &full_bar[stage], cb * BK, c.x0 + kx - 1, c.y0 + ky - 1, c.n_img0);
-            } else {
-              tma_load_2d_2sm(sa, &p.tmA, &full_bar[stage], kb * BK, c.m0);
-            }
-            tma_load_2d_2sm(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0 + rank * b_rows);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          int ca0 = kb * BK, ca1 = c.m0, ca2 = 0, ca3 = 0;
           if (p.conv) {
             int tap = kb / cpb;
             int cb = kb - tap * cpb;
             int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * BK, c.x0 + kx - 1, c.y0 + ky - 1,
-                        c.n_img0);
-          } else {
-            tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BK, c.m0);
+            ca0 = cb * BK; ca1 = c.x0 + kx - 1; ca2 = c.y0 + ky - 1; ca3 = c.n_img0;
           }
-          if (CL > 1)
-            tma_load_2d_mcast(sb + rank * b_rows * (BK * 2), &p.tmB, &full_bar[stage], kb * BK,
-                              c.n0 + rank * b_rows, kMask);
-          else
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0);
+          if (elect_one()) {
+            if (MMA2) {
+              // both CTAs' loads complete_tx on the leader's barrier: it expects 2 x stage_bytes
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+              if (p.conv) tma_load_4d_2sm(sa, &p.tmA, &full_bar[stage], ca0, ca1, ca2, ca3);
+              else tma_load_2d_2sm(sa, &p.tmA, &full_bar[stage], ca0, ca1);
+              tma_load_2d_2sm(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0 + rank * b_rows);
+            } else {
+              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              if (p.conv) tma_load_4d(sa, &p.tmA, &full_bar[stage], ca0, ca1, ca2, ca3);
+              else tma_load_2d(sa, &p.tmA, &full_bar[stage], ca0, ca1);
+              if (CL > 1)
+                tma_load_2d_mcast(sb + rank * b_rows * (BK * 2), &p.tmB, &full_bar[stage], kb * BK,
+                                  c.n0 + rank * b_rows, kMask);
+              else
+                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, c.n0);
+            }
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!MMA2 || rank == 0)) {
+    // warp-uniform loop; one elected lane issues the tcgen05.mma / commit instructions
+    if (!MMA2 || rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(MMA2 ? 2 * BM : BM, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -213,22 +212,28 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc0 = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc0 = umma_desc_sw128(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t adesc = umma_desc_sw128(sa + k * 32, 16, 1024);
-            uint64_t bdesc = umma_desc_sw128(sb + k * 32, 16, 1024);
-            if (MMA2) umma2_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing K by 16 elements = +32 bytes = +2 in the descriptor's (addr >> 4) field
+              if (MMA2) umma2_bf16(tmem_d, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(tmem_d, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem stage (in every cluster CTA that multicasts into it) when these MMAs retire
+            if (MMA2) umma2_commit_mcast(&empty_bar[stage], kMask);
+            else if (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
+            else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue (of both CTAs when paired)
+            if (kb == p.num_kb - 1) {
+              if (MMA2) umma2_commit_mcast(&tfull_bar[buf], kMask);
+              else umma_commit(&tfull_bar[buf]);
+            }
           }
-          // frees the smem stage (in every cluster CTA that multicasts into it) when these MMAs retire
-          if (MMA2) umma2_commit_mcast(&empty_bar[stage], kMask);
-          else if (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue (of both CTAs when paired)
-        if (MMA2) umma2_commit_mcast(&tfull_bar[buf], kMask);
-        else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {

@@ -138,9 +138,11 @@ def _tuning():
     return _TUNING
 
 
-def gemm_key(M, N, K, conv, pair):
+def gemm_key(M, N, K, conv, pair, epi=0):
+    """tuning-table key; epi = 0: 16-bit output, 1: fp32 output, 2: fp32 output + residual (the exposed
+    epilogue of a one-wave launch differs enough between them to change the best tile)"""
     g = f"c{conv['n_img']}x{conv['H']}x{conv['W']}" if conv is not None else "lin"
-    return f"{g}:{M}:{N}:{K}:{int(pair)}"
+    return f"{g}:{M}:{N}:{K}:{int(pair)}:{int(epi)}"
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
@@ -175,7 +177,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.out, g.out_dtype = _p(out), _dt(out)
     g.ld_out = ld_out if ld_out is not None else n_out
     g.act, g.pair = act, pair
-    tuned = _tuning().get(gemm_key(M, N, K, conv, pair)) if (tc and (bn is None or cluster is None)) else None
+    epi = (2 if residual is not None else 1) if out.dtype == torch.float32 else 0
+    key = gemm_key(M, N, K, conv, pair, epi)
+    tuned = _tuning().get(key) if (tc and (bn is None or cluster is None)) else None
     if bn is None:
         bn = default_bn(N, True) if pair else (tuned["bn"] if tuned else choose_bn(M, N, K))
     if cluster is None:
@@ -183,7 +187,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.bn, g.cluster = bn, cluster
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
-    with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=gemm_key(M, N, K, conv, pair),
+    with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=key, epi=epi,
                conv=None if conv is None else (conv["n_img"], conv["H"], conv["W"], conv["Cin"])):
         _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt", lib)
     return out

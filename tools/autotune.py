@@ -2,7 +2,7 @@
 
 Runs one eager step of the chosen workloads with the profiling hook to collect every distinct
 (kind, M, N, K, conv geometry, paired) the step launches, then times each with every admissible tile
-width and both CTA modes (cold L2, median of 9) and writes instantir_b200/tuning_b200.json."""
+width and both CTA modes (R launches on rotating weight copies inside one CUDA graph) and writes instantir_b200/tuning_b200.json."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,7 +29,7 @@ def collect(cfg, latent, B, preview):
     shapes = {}
     for name, work, _, _ in ops.PROFILE:
         if name in ("gemm_tc", "conv3x3_tc"):
-            shapes[work["key"]] = (work["M"], work["N"], work["K"], work["conv"], work["pair"])
+            shapes[work["key"]] = (work["M"], work["N"], work["K"], work["conv"], work["pair"], work["epi"])
     ops.PROFILE = None
     del pipe, unet, agg, loop
     torch.cuda.empty_cache()
@@ -40,25 +40,32 @@ shapes = {}
 shapes.update(collect(pcfg.sdxl(), 128, 1, False))
 shapes.update(collect(pcfg.tiny(), 32, 1, True))
 print(f"{len(shapes)} distinct shapes", flush=True)
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+R = 8  # launches per timed graph, each on its own weight copy (weights stream from HBM in the real step)
 
 
-def timeit(fn, iters=9):
-    for _ in range(2):
+def graph_time(fn, reps=4):
+    """us per launch of fn() = R launches, captured in one CUDA graph (no host launch floor)"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
         fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()
+    best = 1e9
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ts.sort()
-    return ts[len(ts) // 2] * 1e3
+        e0.record(); g.replay(); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best * 1e3 / R
 
 
 table = {}
-for key, (M, N, K, conv, pair) in sorted(shapes.items(), key=lambda kv: -kv[1][0] * kv[1][1] * kv[1][2]):
+for key, (M, N, K, conv, pair, epi) in sorted(shapes.items(), key=lambda kv: -kv[1][0] * kv[1][1] * kv[1][2]):
     if conv is not None:
         n, H, W, Ci = conv
         a = torch.randn(n, H, W, Ci, device=dev, dtype=torch.bfloat16)
@@ -66,9 +73,11 @@ for key, (M, N, K, conv, pair) in sorted(shapes.items(), key=lambda kv: -kv[1][0
     else:
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         cd = None
-    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * K ** -0.5
+    reps = R if N * K * 2 * R < (1 << 30) else 2
+    ws = [torch.randn(N, K, device=dev, dtype=torch.bfloat16) * K ** -0.5 for _ in range(reps)]
     n_out = N // 2 if pair else N
-    out = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if epi else torch.bfloat16)
+    res = out if epi == 2 else None
     aux = torch.randn(M, n_out, device=dev) if pair == ops.PAIR_SFT else None
     bns = [ops.default_bn(N, True)] if pair else list(range(64, 257, 32))
     best = None
@@ -76,7 +85,8 @@ for key, (M, N, K, conv, pair) in sorted(shapes.items(), key=lambda kv: -kv[1][0
         for cl in (1, 2):
             if cl == 2 and (M + 127) // 128 < 2:
                 continue
-            t = timeit(lambda: ops.gemm(a, w, out, M=M, N=N, K=K, pair=pair, aux=aux, bn=bn, conv=cd, cluster=cl))
+            t = graph_time(lambda: [ops.gemm(a, ws[i % reps], out, M=M, N=N, K=K, pair=pair, aux=aux, residual=res, bn=bn,
+                                             conv=cd, cluster=cl) for i in range(R)])
             if best is None or t < best[0]:
                 best = (t, bn, cl)
     table[key] = {"bn": best[1], "cluster": best[2], "us": round(best[0], 1),

@@ -46,6 +46,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
+constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 columns, XOR-swizzled
 
 struct alignas(64) GemmTcParams {
   CUtensorMap tmA;
@@ -54,6 +55,7 @@ struct alignas(64) GemmTcParams {
   int conv, n_img, H, W, Cin;
   int Wt, Ht, Nt, tiles_x, tiles_y, tiles_img;
   int tiles_m, tiles_n, BN, stages;
+  int epi_slots;   // 4 KiB staging slots per epilogue warp (> 1: the fp32 residual tile is prefetched into them)
   int tiles_m_cl;  // ceil(tiles_m / CL): M super-tiles per N tile
   const float* bias;
   const float* rowvec;
@@ -113,6 +115,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(full_bar) + 256;  // 8 epilogue warps x EPI_STAGE_BYTES
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,139 +241,185 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Two phases per 32-column chunk.  ROW phase: TMEM lane == row, so a thread holds 32 consecutive columns
+    // of ONE row (bias, temb row-vector, activation, GEGLU / SFT are applied here).  Writing global memory
+    // from that layout touches 32 different lines per instruction, so the chunk is transposed through a
+    // private, XOR-swizzled 4 KiB shared-memory tile and the COALESCED phase (8 lanes per row, float4 per
+    // lane: four full 128-byte row segments per instruction) adds the residual and stores.
     const int lane_base = (warp & 3) * 32;  // TMEM lane quarter this warp may access
     const int chunk_par = (warp - 2) >> 2;   // which of the two warps of this quarter: odd/even chunks
     const int row = lane_base + lane;
     const int half = p.BN >> 1;
     const int n_out_total = PAIR ? (p.N >> 1) : p.N;
+    const int R = p.epi_slots;
+    uint8_t* stg = epi_stage + (warp - 2) * R * EPI_STAGE_BYTES;
+    // fp32 residual: its tile is fetched into the staging ring with cp.async WHILE the main loop runs, so the
+    // epilogue never waits on global-memory latency (a one-wave launch exposed ~10-25 us of it before)
+    const bool pre = p.residual != nullptr && !p.res_bf16;
+    const int crow = lane >> 3;              // coalesced phase: row within a group of 4
+    const int cc4 = lane & 7;                // coalesced phase: float4 column
     uint32_t acc_i = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
       const uint32_t buf = acc_i & 1;
       const uint32_t acc_phase = (acc_i >> 1) & 1;
       TileCoord c = tile_coord<CL>(p, tile, rank);
-      long long m_out;
-      bool valid;
-      if (p.conv) {
-        int xi = row % p.Wt;
-        int t2 = row / p.Wt;
-        int yi = t2 % p.Ht;
-        int ni = t2 / p.Ht;
-        int x = c.x0 + xi, y = c.y0 + yi, n = c.n_img0 + ni;
-        valid = (x < p.W) && (y < p.H) && (n < p.n_img);
-        m_out = (static_cast<long long>(n) * p.H + y) * p.W + x;
-      } else {
-        m_out = c.m0 + row;
-        valid = m_out < p.M;
-      }
-      const int sample = valid ? static_cast<int>(m_out / p.rows_per_sample) : 0;
+      auto row_to_m = [&](int r) -> long long {  // output row of tile row r, or -1 when outside the matrix
+        if (p.conv) {
+          int xi = r % p.Wt;
+          int t2 = r / p.Wt;
+          int yi = t2 % p.Ht;
+          int ni = t2 / p.Ht;
+          int x = c.x0 + xi, y = c.y0 + yi, n = c.n_img0 + ni;
+          if (x >= p.W || y >= p.H || n >= p.n_img) return -1;
+          return (static_cast<long long>(n) * p.H + y) * p.W + x;
+        }
+        long long m = c.m0 + r;
+        return m < p.M ? m : -1;
+      };
+      const long long m_own = row_to_m(row);
+      const bool valid = m_own >= 0;
+      const int sample = valid ? static_cast<int>(m_own / p.rows_per_sample) : 0;
+      long long mrow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mrow[i] = row_to_m(lane_base + i * 4 + crow);
+
+      const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
+      const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
+      const int nchunks_w = ncols > chunk_par * 32 ? (ncols - chunk_par * 32 + 63) / 64 : 0;  // chunks of this warp
+      auto prefetch = [&](int k) {
+        const int pc = chunk_par * 32 + 64 * k;
+        const int pcol = nout0 + pc + cc4 * 4;
+        const bool ok = (pc + cc4 * 4 < ncols) && (pcol < n_out_total);
+        uint8_t* slot = stg + (k % R) * EPI_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + crow;
+          if (mrow[i] >= 0 && ok)
+            cp_async16(slot + rl * 128 + ((cc4 ^ (rl & 7)) << 4),
+                       reinterpret_cast<const float*>(p.residual) + mrow[i] * p.ld_res + pcol);
+        }
+        cp_async_commit();
+      };
+      if (pre)
+        for (int k = 0; k < R && k < nchunks_w; ++k) prefetch(k);
 
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
-      const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
-      const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
-      for (int cc = chunk_par * 32; cc < ncols; cc += 64) {
+      for (int kc = 0; kc < nchunks_w; ++kc) {
+        const int cc = chunk_par * 32 + 64 * kc;
+        uint8_t* slot = stg + (kc % R) * EPI_STAGE_BYTES;
         uint32_t r[32];
         uint32_t r2[32];
         tmem_ld32(taddr + cc, r);
         if (PAIR) tmem_ld32(taddr + half + cc, r2);
         tmem_ld_wait();
-        if (valid) {
-          float v[32];
-          const int pn = c.n0 + cc;  // packed column of r[0]
+        float v[32];
+        const int pn = c.n0 + cc;  // packed column of r[0]
+        const int on = nout0 + cc;  // output column of v[0]
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (pn + j < p.N) {
-                float4 b = ld4(p.bias + pn + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-          }
-          if (p.rowvec) {
-            const float* rv = p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + pn;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (pn + j < p.N) {
-                float4 b = ld4(rv + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-          }
-          if (p.act == IIR_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-          } else if (p.act == IIR_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
-          }
-          const int on = nout0 + cc;  // output column of v[0]
-          if (PAIR) {
-            float g[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r2[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (pn + half + j < p.N) {
-                  float4 b = ld4(p.bias + pn + half + j);
-                  g[j] += b.x; g[j + 1] += b.y; g[j + 2] += b.z; g[j + 3] += b.w;
-                }
-              }
-            }
-            if (PAIR == IIR_PAIR_GEGLU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
-            } else {  // SFT: h * (gamma + 1) + beta
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (on + j < n_out_total) {
-                  float4 h = p.aux_bf16
-                      ? ld4(reinterpret_cast<const h16*>(p.aux) + m_out * p.ld_aux + on + j)
-                      : ld4(reinterpret_cast<const float*>(p.aux) + m_out * p.ld_aux + on + j);
-                  v[j] = h.x * (v[j] + 1.0f) + g[j];
-                  v[j + 1] = h.y * (v[j + 1] + 1.0f) + g[j + 1];
-                  v[j + 2] = h.z * (v[j + 2] + 1.0f) + g[j + 2];
-                  v[j + 3] = h.w * (v[j + 3] + 1.0f) + g[j + 3];
-                }
-              }
-            }
-          }
-          if (p.residual) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (on + j < n_out_total) {
-                float4 q = p.res_bf16
-                    ? ld4(reinterpret_cast<const h16*>(p.residual) + m_out * p.ld_res + on + j)
-                    : ld4(reinterpret_cast<const float*>(p.residual) + m_out * p.ld_res + on + j);
-                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-              }
-            }
-          }
-          if (p.out_bf16) {
-            h16* o = reinterpret_cast<h16*>(p.out) + m_out * p.ld_out + on;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (on + j < n_out_total) {
-                uint4 u;
-                u.x = pack_bf16(v[j], v[j + 1]);
-                u.y = pack_bf16(v[j + 2], v[j + 3]);
-                u.z = pack_bf16(v[j + 4], v[j + 5]);
-                u.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + m_out * p.ld_out + on;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (on + j < n_out_total)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) {
+            if (pn + j < p.N) {
+              float4 b = ld4(p.bias + pn + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
         }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + pn;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (pn + j < p.N) {
+              float4 b = ld4(rv + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+        }
+        if (p.act == IIR_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        } else if (p.act == IIR_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+        }
+        if (PAIR) {
+          float g[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r2[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (pn + half + j < p.N) {
+                float4 b = ld4(p.bias + pn + half + j);
+                g[j] += b.x; g[j + 1] += b.y; g[j + 2] += b.z; g[j + 3] += b.w;
+              }
+            }
+          }
+          if (PAIR == IIR_PAIR_GEGLU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
+          } else {  // SFT: h * (gamma + 1) + beta
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (valid && on + j < n_out_total) {
+                float4 h = p.aux_bf16
+                    ? ld4(reinterpret_cast<const h16*>(p.aux) + m_own * p.ld_aux + on + j)
+                    : ld4(reinterpret_cast<const float*>(p.aux) + m_own * p.ld_aux + on + j);
+                v[j] = h.x * (v[j] + 1.0f) + g[j];
+                v[j + 1] = h.y * (v[j + 1] + 1.0f) + g[j + 1];
+                v[j + 2] = h.z * (v[j + 2] + 1.0f) + g[j + 2];
+                v[j + 3] = h.w * (v[j + 3] + 1.0f) + g[j + 3];
+              }
+            }
+          }
+        }
+        // ---- transpose through the swizzled staging tile: row `lane`, 16-byte unit (c4 ^ (lane & 7))
+        if (pre) {
+          // groups still allowed in flight: the chunks after this one that were already requested
+          const int issued = kc + R < nchunks_w ? kc + R : nchunks_w;
+          const int pending = issued - (kc + 1);
+          if (pending <= 0) cp_async_wait<0>();
+          else if (pending == 1) cp_async_wait<1>();
+          else if (pending == 2) cp_async_wait<2>();
+          else cp_async_wait<3>();
+          __syncwarp();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4* a4 = reinterpret_cast<float4*>(slot + lane * 128 + ((c4 ^ (lane & 7)) << 4));
+            float4 q = *a4;
+            q.x += v[4 * c4]; q.y += v[4 * c4 + 1]; q.z += v[4 * c4 + 2]; q.w += v[4 * c4 + 3];
+            *a4 = q;
+          }
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<float4*>(slot + lane * 128 + ((c4 ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        }
+        __syncwarp();
+        const int ocol = on + cc4 * 4;
+        const bool col_ok = (cc + cc4 * 4 < ncols) && (ocol < n_out_total);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + crow;
+          float4 x = *reinterpret_cast<const float4*>(slot + rl * 128 + ((cc4 ^ (rl & 7)) << 4));
+          const long long m = mrow[i];
+          if (m >= 0 && col_ok) {
+            if (p.residual && !pre) {
+              float4 q = p.res_bf16
+                  ? ld4(reinterpret_cast<const h16*>(p.residual) + m * p.ld_res + ocol)
+                  : ld4(reinterpret_cast<const float*>(p.residual) + m * p.ld_res + ocol);
+              x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+            }
+            if (p.out_bf16) st4(reinterpret_cast<h16*>(p.out) + m * p.ld_out + ocol, x);
+            else st4(reinterpret_cast<float*>(p.out) + m * p.ld_out + ocol, x);
+          }
+        }
+        __syncwarp();
+        if (pre && kc + R < nchunks_w) prefetch(kc + R);
       }
       tc_fence_before();
       if (MMA2 && rank != 0) mbar_arrive_remote(&tempty_bar[buf], 0);  // the leader's MMA thread waits for both
@@ -515,11 +564,25 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.act = a->act;
 
   const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  // staging slots per epilogue warp: enough for this warp's chunks of the tile when an fp32 residual is
+  // prefetched (at most 3), but never at the price of a shallow main-loop pipeline (measured: a CTA pair
+  // wants >= 6 stages of 26 KB at K = 5120, one CTA >= 4 of 36 KB)
+  int slots = 1;
+  if (a->residual && a->res_dtype == IIR_F32) {
+    const int ncols = a->pair ? a->bn / 2 : a->bn;
+    slots = (ncols + 63) / 64;
+    if (slots > 3) slots = 3;
+    int want = mma2 ? 6 : 4;
+    if (want > p.num_kb + 1) want = p.num_kb + 1;
+    while (slots > 1 && (227 * 1024 - 1024 - 256 - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
+  }
+  p.epi_slots = slots;
+  const int epi_bytes = 8 * slots * EPI_STAGE_BYTES;
+  int stages = (227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
 
   const int num_tiles = p.tiles_m_cl * p.tiles_n;  // super-tiles, one per cluster at a time

@@ -315,6 +315,11 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
 constexpr int ATS_THREADS = 256;
 constexpr int ATS_KV_STAGES = 3;
 
+// PERBLOCK = true: every key segment fits ONE 128-key block (the decoupled text + image cross-attention: 77 and
+// 64 keys).  Block j is segment j with its own K/V tensors; its softmax is complete after that block, so P is
+// normalised (and weighted by seg_scale) in registers and both segments accumulate straight into the same O:
+//   out = sum_s seg_scale[s] * softmax(Q K_s^T) V_s     with no per-segment accumulator and no final rescale.
+template <bool PERBLOCK>
 __global__ void __launch_bounds__(ATS_THREADS, 2)
 attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -335,12 +340,16 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nb = p.nblk[0];
+  const int nb = PERBLOCK ? p.n_seg : p.nblk[0];
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK[0]);
     tma_prefetch_desc(&p.tmV[0]);
+    if (PERBLOCK && p.n_seg > 1) {
+      tma_prefetch_desc(&p.tmK[1]);
+      tma_prefetch_desc(&p.tmV[1]);
+    }
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
     mbar_init(s_empty, 128);
@@ -381,8 +390,9 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
         if (elect_one()) {
           mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-          tma_load_3d(sK + st * TILE_BYTES, &p.tmK[0], &kv_full[st], p.k_off[0] + h * 64, jb * 128, b);
-          tma_load_3d(sV + st * TILE_BYTES, &p.tmV[0], &kv_full[st], p.v_off[0] + h * 64, jb * 128, b);
+          const int sg = PERBLOCK ? jb : 0, jr = PERBLOCK ? 0 : jb * 128;
+          tma_load_3d(sK + st * TILE_BYTES, &p.tmK[sg], &kv_full[st], p.k_off[sg] + h * 64, jr, b);
+          tma_load_3d(sV + st * TILE_BYTES, &p.tmV[sg], &kv_full[st], p.v_off[sg] + h * 64, jr, b);
         }
         __syncwarp();
         if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
@@ -444,7 +454,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
     float m_ref = -INFINITY, l_run = 0.f;
 #pragma unroll 1
     for (int jb = 0; jb < nb; ++jb) {
-      const int valid = min(128, p.kv_len[0] - jb * 128);
+      const int valid = PERBLOCK ? min(128, p.kv_len[jb]) : min(128, p.kv_len[0] - jb * 128);
       mbar_wait(s_full, jb & 1);
       tc_fence_after();
       uint32_t sr[128];
@@ -475,6 +485,40 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(sr[j + c]));
       const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
                              fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      if (PERBLOCK) {
+        // complete softmax of this segment in registers: e -> sum -> P = e * seg_scale / sum
+        const float mneg = -mx * sl2;
+        float sums[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sums[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const float e = ex2_approx(fmaf(__uint_as_float(sr[j]), sl2, mneg));
+          sums[j & 7] += e;
+          sr[j] = __float_as_uint(e);
+        }
+        const float wseg = p.seg_scale[jb] /
+            (((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7])));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            pk[j >> 1] = pack_bf16(__uint_as_float(sr[g * 32 + j]) * wseg, __uint_as_float(sr[g * 32 + j + 1]) * wseg);
+          if (g == 0 || g == 2) {
+            mbar_wait(&p_empty[g >> 1], (jb & 1) ^ 1);
+            tc_fence_after();
+          }
+          tmem_st16(tmem_P + trow + g * 16, pk);
+          if (g == 1 || g == 3) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[g >> 1]);
+          }
+        }
+        l_run = 1.0f;
+        continue;
+      }
       const bool first = (jb == 0);
       const bool grow = !first && (mx > m_ref + kLazy);
       const float m_old = m_ref;
@@ -550,7 +594,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
     // all key blocks done: wait for the last P V, then O / l
     mbar_wait(&p_empty[1], (nb - 1) & 1);
     tc_fence_after();
-    const float w = p.seg_scale[0] / l_run;
+    const float w = PERBLOCK ? 1.0f : p.seg_scale[0] / l_run;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       uint32_t r[32];
@@ -639,9 +683,13 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
     const char* ev = getenv("IIR_ATTN_V1");
     v1 = (ev && ev[0] == '1') ? 1 : 0;
   }
+  const bool one_block_each = a->n_seg == 2 && a->kv_len[0] <= 128 && a->kv_len[1] <= 128;
   if (a->n_seg == 1 && !v1) {
-    e = cudaFuncSetAttribute(attn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel, grid, dim3(ATS_THREADS), smem, st, p);
+    e = cudaFuncSetAttribute(attn_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<false>, grid, dim3(ATS_THREADS), smem, st, p);
+  } else if (one_block_each && !v1) {
+    e = cudaFuncSetAttribute(attn_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<true>, grid, dim3(ATS_THREADS), smem, st, p);
   } else if (a->n_seg == 1) {
     e = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = launch_pdl(attn_tc_kernel<1>, grid, dim3(ATT_THREADS), smem, st, p);

@@ -218,8 +218,11 @@ def test_self_attention_fused_qkv(tc, B, heads, n):
 
 
 @pytest.mark.parametrize("tc", [True, False])
-def test_decoupled_cross_attention_two_segments(tc):
-    B, heads, n, nt, ni, scale_ip = 2, 2, 256, 77, 64, 0.7
+@pytest.mark.parametrize("nt,ni", [(77, 64), (200, 64), (128, 1)])
+def test_decoupled_cross_attention_two_segments(tc, nt, ni):
+    """(77, 64): both segments fit one key block -> the normalise-in-registers kernel; (200, 64): the
+    multi-block two-segment kernel; (128, 1): a full block next to a single key"""
+    B, heads, n, scale_ip = 2, 2, 256, 0.7
     C = heads * 64
     dt = torch.bfloat16 if tc else torch.float32
     q = rnd(B, n, C, seed=1, dtype=dt)

@@ -127,7 +127,10 @@ int iir_attn_simt(const iir_attn_args* args, void* stream);
  * Normalisation
  * ---------------------------------------------------------------------------------------- */
 /* GroupNorm(32 groups) [+ SiLU] over NHWC x [n_img, HW, C]: module/min_sdxl.py:245,250,568,838.
- * `partials` is caller-owned scratch of iir_groupnorm_scratch_floats(...) floats.          */
+ * `partials` is caller-owned scratch of iir_groupnorm_scratch_floats(...) floats that must be
+ * ZERO-FILLED before its first use (it ends with one ticket counter per image: the last row-chunk of
+ * an image to finish reduces the partial sums, in a fixed order); every call leaves the counters zero,
+ * so the same scratch can be reused by later calls on the same stream.                        */
 int64_t iir_groupnorm_scratch_floats(int n_img, int groups);
 int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* out,
                   int out_dtype, int n_img, int HW, int C, int groups, float eps, int silu,

@@ -9,68 +9,142 @@ namespace {
 constexpr int GN_MAX_CHUNKS = 256;
 constexpr int GN_THREADS = 256;
 
-// ---- stage 1: per (image, row-chunk) partial sum / sum of squares for every group ------------
-// grid (chunks, n_img); thread t: vector lane tv = t%64 walks channel vectors, row lane tr = t/64.
+// 16-byte vectors: 4 fp32 or 8 16-bit channels per thread and access
+template <typename T> struct V16 { static constexpr int N = 16 / sizeof(T); };
+// raw 16-byte load (kept packed while in flight: 4 registers), expanded to floats only when consumed
 template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, int HW, int C, int groups,
-                int rows_per_chunk) {
-  extern __shared__ float sm[];  // [4][C] sums, [4][C] squares
-  pdl_trigger();
-  pdl_wait();
-  float* s_sum = sm;
-  float* s_sq = sm + 4 * C;
-  const int chunk = blockIdx.x, img = blockIdx.y;
-  const int tv = threadIdx.x & 63, tr = threadIdx.x >> 6;
-  const int cv = C >> 2;
-  const int r0 = chunk * rows_per_chunk;
-  const int r1 = min(HW, r0 + rows_per_chunk);
-  const T* base = x + static_cast<long long>(img) * HW * C;
-  for (int v = tv; v < cv; v += 64) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (int r = r0 + tr; r < r1; r += 4) {
-      float4 a = ld4(base + static_cast<long long>(r) * C + v * 4);
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      q.x += a.x * a.x; q.y += a.y * a.y; q.z += a.z * a.z; q.w += a.w * a.w;
-    }
-    float* ps = s_sum + tr * C + v * 4;
-    float* pq = s_sq + tr * C + v * 4;
-    ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
-    pq[0] = q.x; pq[1] = q.y; pq[2] = q.z; pq[3] = q.w;
-  }
-  __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
-    double s = 0.0, q = 0.0;
-    for (int tr2 = 0; tr2 < 4; ++tr2)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        s += s_sum[tr2 * C + c];
-        q += s_sq[tr2 * C + c];
-      }
-    float* o = partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + chunk) * groups + g) * 2;
-    o[0] = static_cast<float>(s);
-    o[1] = static_cast<float>(q);
+__device__ __forceinline__ uint4 ldraw(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void expand(const uint4& u, float (&v)[4], const float*) {
+  v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+}
+__device__ __forceinline__ void expand(const uint4& u, float (&v)[8], const h16*) {
+  const h162* h = reinterpret_cast<const h162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = h162_to_ff(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T, int N>
+__device__ __forceinline__ void ldv(const T* p, float (&v)[N]) { expand(ldraw(p), v, p); }
+template <int N>
+__device__ __forceinline__ void stv(float* p, const float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <int N>
+__device__ __forceinline__ void stv(h16* p, const float (&v)[N]) {
+  static_assert(N == 4 || N == 8, "4 or 8 channels per thread");
+  if constexpr (N == 8) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    uint2 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
   }
 }
 
-// ---- stage 1b: fixed-order reduction of the chunk partials -> (mean, rstd) per (image, group) ----
-__global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats, int groups,
-                   int nchunks, double count, float eps) {
-  // 8 sub-lanes per group each sum every 8th chunk, then the 8 sub-sums are combined in a fixed
-  // order: deterministic, and only nchunks/8 dependent adds deep.
-  __shared__ double sh_s[64][8], sh_q[64][8];
+// Thread layout shared by both stages: block = TX x TY threads, tx owns ONE 16-byte channel vector per pass
+// (pass p: vector p*TX + tx), ty walks the rows of the block's chunk with stride TY, four rows in flight.
+// A warp reads 512 contiguous bytes of a row; per-channel state (sums / scale, shift) lives in registers.
+
+// ---- stage 1: per (image, row-chunk) partial sum / sum of squares for every group; the LAST chunk of an
+// image to finish (ticket counter) reduces all partials in a fixed order into (mean, rstd) — no separate
+// finalize launch, and still deterministic.
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, float* __restrict__ stats,
+                unsigned int* __restrict__ tickets, int HW, int C, int groups, int rows_per_chunk,
+                int nchunks, double count, float eps, int TX, int TY) {
+  constexpr int N = V16<T>::N;
+  extern __shared__ float sm[];  // [TY][C] sums, [TY][C] squares
+  __shared__ double sh_s[32][8], sh_q[32][8];
+  __shared__ int s_last;
   pdl_trigger();
   pdl_wait();
-  const int img = blockIdx.x;
-  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  for (int g0 = 0; g0 < groups; g0 += 32) {
+  float* s_sum = sm;
+  float* s_sq = sm + TY * C;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;  // ty >= TY: surplus thread of the last warp (idle in the data loop)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nthreads = blockDim.x;
+  const int cv = ty < TY ? C / N : 0;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  const T* base = x + static_cast<long long>(img) * HW * C;
+  for (int v = tx; v < cv; v += TX) {
+    float s[N], q[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) s[j] = q[j] = 0.f;
+    int r = r0 + ty;
+    const T* ptr = base + static_cast<long long>(r) * C + v * N;
+    const long long step = static_cast<long long>(TY) * C;
+    for (; r + 3 * TY < r1; r += 4 * TY, ptr += 4 * step) {  // four independent 16-byte loads in flight
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = ldraw(ptr + u * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a[N];
+        expand(raw[u], a, ptr);
+#pragma unroll
+        for (int j = 0; j < N; ++j) { s[j] += a[j]; q[j] = fmaf(a[j], a[j], q[j]); }
+      }
+    }
+    for (; r < r1; r += TY, ptr += step) {
+      float a[N];
+      ldv(ptr, a);
+#pragma unroll
+      for (int j = 0; j < N; ++j) { s[j] += a[j]; q[j] = fmaf(a[j], a[j], q[j]); }
+    }
+    stv<N>(s_sum + ty * C + v * N, s);
+    stv<N>(s_sq + ty * C + v * N, q);
+  }
+  __syncthreads();
+  // one warp per group: lanes stride over the TY x cpg per-channel sums, fixed-order shuffle tree
+  const int cpg = C / groups;
+  const int nwarps = nthreads >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < TY * cpg; i += 32) {
+      const int t2 = i / cpg, c = g * cpg + (i - t2 * cpg);
+      s += s_sum[t2 * C + c];
+      q += s_sq[t2 * C + c];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    if (lane == 0) {
+      float* o = partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + chunk) * groups + g) * 2;
+      o[0] = s;
+      o[1] = q;
+    }
+  }
+  // ---- last chunk of this image: reduce the chunk partials
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[img], 1u);
+    s_last = (t == static_cast<unsigned int>(nchunks) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // sub-lanes of a group each sum every SUB-th chunk, then the sub-sums are combined in a fixed order:
+  // deterministic whichever chunk happens to finish last
+  const int SUB = 8;
+  const int gpp = nthreads / SUB;  // groups per pass
+  const int g = threadIdx.x / SUB, sub = threadIdx.x % SUB;
+  for (int g0 = 0; g0 < groups; g0 += gpp) {
     const int gg = g0 + g;
+    const bool act = g < gpp && gg < groups && g < 32;
     double s = 0.0, q = 0.0;
-    if (gg < groups) {
-      for (int ch = sub; ch < nchunks; ch += 8) {
-        const float2 pp = *reinterpret_cast<const float2*>(
-            partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + ch) * groups + gg) * 2);
+    if (act) {
+      for (int ch = sub; ch < nchunks; ch += SUB) {
+        const float2 pp = __ldcg(reinterpret_cast<const float2*>(
+            partials + ((static_cast<long long>(img) * GN_MAX_CHUNKS + ch) * groups + gg) * 2));
         s += pp.x;
         q += pp.y;
       }
@@ -78,9 +152,9 @@ gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats
       sh_q[g][sub] = q;
     }
     __syncthreads();
-    if (gg < groups && sub == 0) {
+    if (act && sub == 0) {
       s = q = 0.0;
-      for (int k = 0; k < 8; ++k) { s += sh_s[g][k]; q += sh_q[g][k]; }
+      for (int k = 0; k < SUB; ++k) { s += sh_s[g][k]; q += sh_q[g][k]; }
       double mean = s / count;
       double var = q / count - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -90,15 +164,16 @@ gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) tickets[img] = 0u;  // self-resetting: the scratch is reusable by the next call
 }
 
 // ---- stage 2: normalise, affine, optional SiLU ---------------------------------------------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const float* __restrict__ partials,
-                TO* __restrict__ out, int HW, int C, int groups, int nchunks, float eps, int silu,
-                int rows_per_block) {
+                const float* __restrict__ beta, const float* __restrict__ stats,
+                TO* __restrict__ out, int HW, int C, int groups, int silu, int rows_per_block, int TX, int TY) {
+  constexpr int N = V16<TI>::N;
   extern __shared__ float sm[];  // [C] scale, [C] shift
   pdl_trigger();
   pdl_wait();
@@ -106,31 +181,58 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
   float* s_shift = sm + C;
   const int img = blockIdx.y;
   const int cpg = C / groups;
-  const float* s_stats = partials + static_cast<long long>(img) * groups * 2;  // (mean, rstd) pairs
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    int g = c / cpg;
-    float sc = s_stats[2 * g + 1] * (gamma ? gamma[c] : 1.0f);
+  const float* s_stats = stats + static_cast<long long>(img) * groups * 2;  // (mean, rstd) pairs
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_stats[2 * g + 1] * (gamma ? gamma[c] : 1.0f);
     s_scale[c] = sc;
     s_shift[c] = (beta ? beta[c] : 0.0f) - s_stats[2 * g] * sc;
   }
   __syncthreads();
-  const int cv = C >> 2;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int cv = ty < TY ? C / N : 0;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
-  const long long total = static_cast<long long>(r1 - r0) * cv;
-  const TI* xb = x + (static_cast<long long>(img) * HW + r0) * C;
-  TO* ob = out + (static_cast<long long>(img) * HW + r0) * C;
-  for (long long i = threadIdx.x; i < total; i += GN_THREADS) {
-    int v = static_cast<int>(i % cv);
-    float4 a = ld4(xb + i * 4);
-    const float* sc = s_scale + v * 4;
-    const float* sh = s_shift + v * 4;
-    a.x = a.x * sc[0] + sh[0];
-    a.y = a.y * sc[1] + sh[1];
-    a.z = a.z * sc[2] + sh[2];
-    a.w = a.w * sc[3] + sh[3];
-    if (silu) { a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w); }
-    st4(ob + i * 4, a);
+  const TI* xb = x + static_cast<long long>(img) * HW * C;
+  TO* ob = out + static_cast<long long>(img) * HW * C;
+  const long long step = static_cast<long long>(TY) * C;
+  for (int v = tx; v < cv; v += TX) {
+    float sc[N], sh[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 4) {
+      float4 a = *reinterpret_cast<const float4*>(s_scale + v * N + j);
+      float4 b = *reinterpret_cast<const float4*>(s_shift + v * N + j);
+      sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
+      sh[j] = b.x; sh[j + 1] = b.y; sh[j + 2] = b.z; sh[j + 3] = b.w;
+    }
+    auto apply = [&](float (&a)[N]) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        a[j] = fmaf(a[j], sc[j], sh[j]);
+        if (silu) a[j] = silu_fast(a[j]);
+      }
+    };
+    int r = r0 + ty;
+    const TI* ptr = xb + static_cast<long long>(r) * C + v * N;
+    TO* optr = ob + static_cast<long long>(r) * C + v * N;
+    for (; r + 3 * TY < r1; r += 4 * TY, ptr += 4 * step, optr += 4 * step) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = ldraw(ptr + u * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a[N];
+        expand(raw[u], a, ptr);
+        apply(a);
+        stv<N>(optr + u * step, a);
+      }
+    }
+    for (; r < r1; r += TY, ptr += step, optr += step) {
+      float a[N];
+      ldv(ptr, a);
+      apply(a);
+      stv<N>(optr, a);
+    }
   }
 }
 
@@ -272,8 +374,9 @@ using namespace iir;
 typedef h16 bf16;
 
 extern "C" int64_t iir_groupnorm_scratch_floats(int n_img, int groups) {
-  // chunk partials followed by the finalised (mean, rstd) table
-  return static_cast<int64_t>(n_img) * GN_MAX_CHUNKS * groups * 2 + static_cast<int64_t>(n_img) * groups * 2;
+  // chunk partials, the finalised (mean, rstd) table, and one ticket counter per image.  The ticket words
+  // must be ZERO before the first call; every call leaves them zero again.
+  return static_cast<int64_t>(n_img) * GN_MAX_CHUNKS * groups * 2 + static_cast<int64_t>(n_img) * groups * 2 + n_img;
 }
 
 extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta,
@@ -284,53 +387,59 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   IIR_REQUIRE(n_img > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64 && C % groups == 0 &&
                   C % 4 == 0,
               "iir_groupnorm: bad shape n=%d HW=%d C=%d G=%d", n_img, HW, C, groups);
-  IIR_REQUIRE(8 * C * sizeof(float) <= 200 * 1024, "iir_groupnorm: C=%d too large", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // enough chunks to fill the machine, at most GN_MAX_CHUNKS, at least 16 rows each
-  int want = (4 * sm_count() + n_img - 1) / n_img;
-  int nchunks = want < 1 ? 1 : (want > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : want);
-  int rpc = (HW + nchunks - 1) / nchunks;
-  if (rpc < 8) rpc = 8;
-  nchunks = (HW + rpc - 1) / rpc;
-  size_t smem1 = 8 * (size_t)C * sizeof(float);
+  // thread layout: TX channel-vector lanes (one 16-byte vector per lane and pass), TY row lanes
+  const int vecn = x_dtype == IIR_F32 ? 4 : 8;
+  IIR_REQUIRE(C % vecn == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "iir_groupnorm: C=%d must be a multiple of %d and x/out 16-byte aligned", C, vecn);
+  const int cv = C / vecn;
+  const int passes = (cv + GN_THREADS - 1) / GN_THREADS;
+  const int TX = (cv + passes - 1) / passes;
+  const int TY = GN_THREADS / TX < 1 ? 1 : GN_THREADS / TX;
+  const int threads = (TX * TY + 31) / 32 * 32;  // whole warps (the shuffle reductions need them)
+  // rows per block: every thread gets >= 8 rows per pass when the image is big enough for ~6 blocks per SM
+  auto rows_for = [&](int max_blocks) {
+    int blocks = (6 * sm_count() + n_img - 1) / n_img;
+    if (blocks > max_blocks) blocks = max_blocks;
+    int r = (HW + blocks - 1) / blocks;
+    if (r < 8 * TY) r = 8 * TY;
+    if (r > HW) r = HW;
+    return r;
+  };
+  const int rpc = rows_for(GN_MAX_CHUNKS);
+  const int nchunks = (HW + rpc - 1) / rpc;
+  size_t smem1 = 2 * (size_t)TY * C * sizeof(float);
+  IIR_REQUIRE(smem1 <= 200 * 1024, "iir_groupnorm: C=%d too large", C);
   dim3 g1(nchunks, n_img);
+  float* stats = partials + static_cast<long long>(n_img) * GN_MAX_CHUNKS * groups * 2;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats + static_cast<long long>(n_img) * groups * 2);
+  const double count = static_cast<double>(HW) * (C / groups);
   cudaError_t e = cudaSuccess;
   if (x_dtype == IIR_F32) {
-    if (smem1 > 48 * 1024)
+    if (smem1 > 40 * 1024)
       e = cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<float>, g1, dim3(GN_THREADS), smem1, st, reinterpret_cast<const float*>(x), partials, HW, C, groups, rpc);
+    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<float>, g1, dim3(threads), smem1, st, reinterpret_cast<const float*>(x), partials, stats, tickets, HW, C, groups, rpc, nchunks, count, eps, TX, TY);
   } else {
-    if (smem1 > 48 * 1024)
+    if (smem1 > 40 * 1024)
       e = cudaFuncSetAttribute(gn_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<bf16>, g1, dim3(GN_THREADS), smem1, st, reinterpret_cast<const bf16*>(x), partials, HW, C, groups, rpc);
+    if (e == cudaSuccess) e = launch_pdl(gn_stats_kernel<bf16>, g1, dim3(threads), smem1, st, reinterpret_cast<const bf16*>(x), partials, stats, tickets, HW, C, groups, rpc, nchunks, count, eps, TX, TY);
   }
   if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   int rc = check_launch("iir_groupnorm(stats)");
   if (rc) return rc;
-  float* stats = partials + static_cast<long long>(n_img) * GN_MAX_CHUNKS * groups * 2;
-  e = launch_pdl(gn_finalize_kernel, dim3(n_img), dim3(256), 0, st, (const float*)partials, stats, groups, nchunks,
-                 static_cast<double>(HW) * (C / groups), eps);
-  if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
-  count_launch();
-  rc = check_launch("iir_groupnorm(finalize)");
-  if (rc) return rc;
-  // apply: blocks of >= 8 rows, ~8 CTAs per SM
-  int blocks_per_img = (8 * sm_count() + n_img - 1) / n_img;
-  int rpb = (HW + blocks_per_img - 1) / blocks_per_img;
-  if (rpb < 8) rpb = 8;
-  blocks_per_img = (HW + rpb - 1) / rpb;
-  dim3 g2(blocks_per_img, n_img);
-  size_t smem2 = 2 * (size_t)C * sizeof(float);
+  const int rpb = rows_for(1 << 30);
+  dim3 g2((HW + rpb - 1) / rpb, n_img);
 #define GO(TI, TO)                                                                                 \
-  e = launch_pdl(gn_apply_kernel<TI, TO>, g2, dim3(GN_THREADS), smem2, st,                        \
+  e = launch_pdl(gn_apply_kernel<TI, TO>, g2, dim3(threads), 2 * (size_t)C * sizeof(float), st,                             \
       reinterpret_cast<const TI*>(x), gamma, beta, (const float*)stats, reinterpret_cast<TO*>(out), HW, C, \
-      groups, nchunks, eps, silu, rpb)
+      groups, silu, rpb, TX, TY)
   if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
   else if (x_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
   else if (x_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
   else GO(bf16, bf16);
 #undef GO
+  if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   return check_launch("iir_groupnorm(apply)");
 }

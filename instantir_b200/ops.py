@@ -230,11 +230,22 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
     return out
 
 
+_GN_SCRATCH = {}
+
+
 def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
-    # allocated per call (a few KiB from torch's caching allocator): a cached buffer would tie CUDA
-    # graphs captured at different times to one another's memory pools
-    need = int(_lib.load().iir_groupnorm_scratch_floats(n_img, groups))
-    return torch.empty(need, dtype=torch.float32, device=device)
+    """GroupNorm scratch (chunk partials, stats, per-image ticket counters).  The ticket words have to be
+    zero before the first call and every call leaves them zero, so one zero-initialised buffer per
+    (device, n_img, groups) is kept for the life of the process; launches are stream-ordered, so reuse by
+    consecutive GroupNorms on a stream is safe."""
+    key = (torch.device(device).index, n_img, groups)
+    buf = _GN_SCRATCH.get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.IIRError("GroupNorm scratch must be created before CUDA-graph capture: run the op once eagerly first")
+        need = int(_lib.load().iir_groupnorm_scratch_floats(n_img, groups))
+        buf = _GN_SCRATCH[key] = torch.zeros(need, dtype=torch.float32, device=device)
+    return buf
 
 
 def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int = 32,

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_symbol():
         assert hasattr(lib, name), name
     assert lib.iir_abi_version() == _lib.ABI_VERSION
     assert isinstance(lib.iir_launch_count(), int)
-    assert lib.iir_groupnorm_scratch_floats(2, 32) == 2 * 256 * 32 * 2 + 2 * 32 * 2
+    assert lib.iir_groupnorm_scratch_floats(2, 32) == 2 * 256 * 32 * 2 + 2 * 32 * 2 + 2
 
 
 def test_struct_layout_matches_header(tmp_path):

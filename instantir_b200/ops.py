@@ -27,8 +27,12 @@ class _Prof:
 
     def __enter__(self):
         if PROFILE is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e1 = torch.cuda.Event(enable_timing=True)
+            # under CUDA-graph capture the events become event-record NODES of the graph (external=True):
+            # after a replay they hold the in-graph start/end of this launch — no host launch gap inside
+            ext = torch.cuda.is_current_stream_capturing()
+            self.work["in_graph"] = ext
+            self.e0 = torch.cuda.Event(enable_timing=True, external=ext)
+            self.e1 = torch.cuda.Event(enable_timing=True, external=ext)
             self.e0.record()
         return self
 

@@ -270,7 +270,8 @@ class GroupNorm:
 
     def __call__(self, x: FMap, silu: bool) -> FMap:
         out = self.rt.empty(x.M, x.C)
-        ops.groupnorm(x.t, self.g, self.b, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups, eps=self.eps, silu=silu)
+        ops.groupnorm(x.t, self.g, self.b, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups, eps=self.eps, silu=silu,
+                      scratch_owner=id(self.rt))
         return FMap(out, x.n, x.H, x.W, x.C)
 
 

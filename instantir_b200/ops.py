@@ -237,12 +237,13 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
 _GN_SCRATCH = {}
 
 
-def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
+def _gn_partials(device, n_img: int, groups: int, owner=None) -> torch.Tensor:
     """GroupNorm scratch (chunk partials, stats, per-image ticket counters).  The ticket words have to be
     zero before the first call and every call leaves them zero, so one zero-initialised buffer per
-    (device, n_img, groups) is kept for the life of the process; launches are stream-ordered, so reuse by
-    consecutive GroupNorms on a stream is safe."""
-    key = (torch.device(device).index, n_img, groups)
+    (device, n_img, groups, owner) is kept for the life of the process; launches are stream-ordered, so reuse
+    by consecutive GroupNorms on a stream is safe.  `owner` separates models that may run CONCURRENTLY on
+    different streams (the pipeline overlaps the UNet's down path with the Aggregator)."""
+    key = (torch.device(device).index, n_img, groups, owner)
     buf = _GN_SCRATCH.get(key)
     if buf is None:
         if torch.cuda.is_current_stream_capturing():
@@ -253,9 +254,9 @@ def _gn_partials(device, n_img: int, groups: int) -> torch.Tensor:
 
 
 def groupnorm(x, gamma, beta, out, *, n_img: int, HW: int, C: int, groups: int = 32,
-              eps: float = 1e-5, silu: bool = False):
+              eps: float = 1e-5, silu: bool = False, scratch_owner=None):
     lib = _L(x, out)
-    part = _gn_partials(x.device, n_img, groups)
+    part = _gn_partials(x.device, n_img, groups, scratch_owner)
     with _Prof("groupnorm", bytes=float(n_img) * HW * C * (2 * x.element_size() + out.element_size())):
         _lib.check(lib.iir_groupnorm(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")),
                                      _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _p(part),

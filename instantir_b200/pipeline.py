@@ -140,7 +140,7 @@ class InstantIRPipeline:
                  init_latents_with_lq=True, multistep_restore=False, adastep_restore=False, previewer_scheduler=None,
                  preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                  controlnet_conditioning_scale=1.0, reference_latents=None, use_cuda_graph=True, cfg_parallel=None,
-                 dp_shard=None, record=None, **kwargs):
+                 dp_shard=None, record=None, overlap_streams=True, **kwargs):
         if prompt is not None or negative_prompt is not None or ip_adapter_image is not None:
             raise NotImplementedError("text / image encoders are outside this build's scope (SURVEY §8 f1-f2): pass "
                                       "prompt_embeds, pooled_prompt_embeds, ip_adapter_image_embeds and a latent `image`")
@@ -245,6 +245,26 @@ class InstantIRPipeline:
                     return unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added, return_dict=False)[0]
                 return run
 
+            S.side = torch.cuda.Stream(device=dev)
+
+            def f_step(cond):
+                """Aggregator + UNet as ONE graph with a fork: the UNet's embeddings, down blocks and mid block do
+                not read the Aggregator's residuals (they enter the up path), so that half runs on a second
+                stream while the Aggregator runs on the first; both are chains of small, under-filled kernels
+                and overlap well (tools/bench_streams.py)."""
+                def run():
+                    cur = torch.cuda.current_stream()
+                    S.side.wait_stream(cur)
+                    with torch.cuda.stream(S.side):
+                        state = unet.forward_down_mid(x_in, t_dev, prompt_all, added_cond_kwargs=added)
+                    down, mid = agg(image_all, t_dev, encoder_hidden_states=prompt_all, controlnet_cond=cond,
+                                    added_cond_kwargs=agg_added, return_dict=False)
+                    cur.wait_stream(S.side)
+                    eps = unet.forward_up(state, down, mid, cond_scale)[0]
+                    return eps, down, mid
+                return run
+
+            S.g_step = {"prev": _Graphed(f_step(preview_latent), use_cuda_graph), "lq": _Graphed(f_step(image_all), use_cuda_graph)}
             S.g_preview = _Graphed(f_preview, use_cuda_graph)
             S.g_agg_prev = _Graphed(f_agg(preview_latent), use_cuda_graph)
             S.g_agg_lq = _Graphed(f_agg(image_all), use_cuda_graph)
@@ -257,6 +277,7 @@ class InstantIRPipeline:
             S.st.down = S.st.mid = None
         x_in, t_dev, cond_scale, preview_latent, st = S.x_in, S.t_dev, S.cond_scale, S.preview_latent, S.st
         g_preview, g_agg_prev, g_agg_lq, g_unet_res, g_unet_plain = S.g_preview, S.g_agg_prev, S.g_agg_lq, S.g_unet_res, S.g_unet_plain
+        g_step = S.g_step if overlap_streams else None
         unet.refresh_context(S.prompt_all, S.added, None)
         loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts)
 
@@ -270,6 +291,7 @@ class InstantIRPipeline:
             cs = min(1.0, float(scales[i])) * keep[i]  # preview_factor == 1 without adastep_restore
             cond_scale.fill_(cs)
             previewed = False
+            noise_pred = None
             if cs > 0.1:  # the `(cond_scale>0.1).sum().item() > 0` gate (:1542), decided on the host
                 if previewing[i] > 0:
                     preview_noise = g_preview()
@@ -277,12 +299,16 @@ class InstantIRPipeline:
                     previewed = True
                     if save_preview_row:
                         loop.preview_row.append(preview_latent[-B:].clone())
-                    st.down, st.mid = g_agg_prev()
                     loop.res_src = "prev"
                 else:
-                    st.down, st.mid = g_agg_lq()
                     loop.res_src = "lq"
-            if st.down is None:
+                if g_step is not None:
+                    noise_pred, st.down, st.mid = g_step[loop.res_src]()   # aggregator || UNet down+mid, then UNet up
+                else:
+                    st.down, st.mid = (g_agg_prev if previewed else g_agg_lq)()
+            if noise_pred is not None:
+                pass
+            elif st.down is None:
                 if cs > 0:
                     raise RuntimeError("control is active but no aggregator features exist")
                 noise_pred = g_unet_plain()  # reference would raise NameError here; UNet-only is the intent

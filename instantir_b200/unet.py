@@ -329,6 +329,15 @@ class UNet2DConditionModel(_EmbeddingMixin):
         """sample [n,4,h,w] fp32 NCHW -> (eps [n,4,h,w] fp32,).  `additional_residual_scale` [n] (fp32)
         is an extension: residuals are multiplied by it inside the fused concat kernel instead of by
         separate elementwise kernels (pipelines/sdxl_instantir.py:1602-1603)."""
+        state = self.forward_down_mid(sample, timestep, encoder_hidden_states, cross_attention_kwargs=cross_attention_kwargs,
+                                      added_cond_kwargs=added_cond_kwargs)
+        return self.forward_up(state, down_block_additional_residuals, mid_block_additional_residual,
+                               additional_residual_scale)
+
+    def forward_down_mid(self, sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None):
+        """First half of forward(): embeddings, conv_in, down blocks and the mid block.  None of it reads the
+        ControlNet-style residuals (they enter the skip connections and the mid output in forward_up), so the
+        pipeline runs this half on a second stream WHILE the Aggregator computes them."""
         rt, cfg = self.rt, self.cfg
         rt.new_forward()
         n, _, H, W = sample.shape
@@ -347,6 +356,16 @@ class UNet2DConditionModel(_EmbeddingMixin):
         for blk in self.down_blocks:
             x, outs = blk(x, temb_act, ehs, kw)
             skips += outs
+        x = self.mid_block(x, temb_act, ehs, kw)
+        return SimpleNamespace(x=x, skips=skips, temb_act=temb_act, ehs=ehs, kw=kw, n=n, H=H, W=W)
+
+    def forward_up(self, state, down_block_additional_residuals=None, mid_block_additional_residual=None,
+                   additional_residual_scale=None):
+        """Second half of forward(): residual injection (fused into the up path's concat), up blocks, conv_out."""
+        rt, cfg = self.rt, self.cfg
+        x, skips, temb_act, ehs, kw = state.x, list(state.skips), state.temb_act, state.ehs, state.kw
+        n, H, W = state.n, state.H, state.W
+        ch0 = cfg.block_out_channels[0]
         is_controlnet = mid_block_additional_residual is not None and down_block_additional_residuals is not None
         residuals = [None] * len(skips)
         mid_res = None
@@ -356,7 +375,6 @@ class UNet2DConditionModel(_EmbeddingMixin):
             mid_res = fmap_from_nchw(mid_block_additional_residual)
             if additional_residual_scale is not None:
                 cond_scale = additional_residual_scale.to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
-        x = self.mid_block(x, temb_act, ehs, kw)
         for blk in self.up_blocks:
             x = blk(x, skips, residuals, mid_res, cond_scale, temb_act, ehs, kw)
             mid_res = None

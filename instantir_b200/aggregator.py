@@ -93,7 +93,10 @@ class Aggregator(_EmbeddingMixin):
 
     def forward(self, sample, timestep, encoder_hidden_states=None, controlnet_cond=None, cat_dim=-2,
                 conditioning_scale=1.0, class_labels=None, timestep_cond=None, attention_mask=None,
-                added_cond_kwargs=None, cross_attention_kwargs=None, return_dict=False):
+                added_cond_kwargs=None, cross_attention_kwargs=None, return_dict=False, head_stream=None):
+        """`head_stream` (extension): the SFT heads of every down block but the last are enqueued on that stream as
+        soon as the block's skip tensors exist, so they overlap the rest of the trunk; the CALLER joins
+        `head_stream` before reading the returned residuals."""
         if self.config.controlnet_conditioning_channel_order != "rgb":
             raise ValueError(f"unknown `controlnet_conditioning_channel_order`: {self.config.controlnet_conditioning_channel_order}")
         if cat_dim not in (-2, 2):
@@ -115,11 +118,22 @@ class Aggregator(_EmbeddingMixin):
         x = FMap(canvas, n, 2 * H, W, ch0)
         skips = [x]
         kw = dict(cross_attention_kwargs or {})
-        for blk in self.down_blocks:
+        down = [None] * len(self.controlnet_down_blocks)
+        done = 0
+        for bi, blk in enumerate(self.down_blocks):
             x, outs = blk(x, temb_act, None, kw)
             skips += outs
+            if head_stream is not None and bi < len(self.down_blocks) - 1:
+                ev = torch.cuda.Event()
+                ev.record()
+                head_stream.wait_event(ev)
+                with torch.cuda.stream(head_stream):
+                    for i in range(done, len(skips)):
+                        down[i] = self.controlnet_down_blocks[i](skips[i])
+                done = len(skips)
         x = self.mid_block(x, temb_act, None, kw)
-        down = [head(s) for s, head in zip(skips, self.controlnet_down_blocks)]
+        for i in range(done, len(skips)):
+            down[i] = self.controlnet_down_blocks[i](skips[i])
         mid = self.controlnet_mid_block(x)
         if not return_dict:
             return (down, mid)

@@ -455,7 +455,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
 #pragma unroll 1
     for (int jb = 0; jb < nb; ++jb) {
       const int valid = PERBLOCK ? min(128, p.kv_len[jb]) : min(128, p.kv_len[0] - jb * 128);
-      mbar_wait(s_full, jb & 1);
+      mbar_wait_sleep(s_full, jb & 1, 20000);
       tc_fence_after();
       uint32_t sr[128];
       {

@@ -163,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         TileCoord c = tile_coord<CL>(p, tile, rank);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 20000);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
           int ca0 = kb * BK, ca1 = c.m0, ca2 = 0, ca3 = 0;
@@ -207,11 +207,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
         const uint32_t buf = acc_i & 1;
         const uint32_t acc_phase = (acc_i >> 1) & 1;
-        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        mbar_wait_sleep(&tempty_bar[buf], acc_phase ^ 1, 20000);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * ACC_STRIDE;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_sleep(&full_bar[stage], phase, 20000);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -303,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       if (pre)
         for (int k = 0; k < R && k < nchunks_w; ++k) prefetch(k);
 
-      mbar_wait(&tfull_bar[buf], acc_phase);
+      mbar_wait_sleep(&tfull_bar[buf], acc_phase, 100000);  // a whole main loop: sleep, do not spin (power)
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
       for (int kc = 0; kc < nchunks_w; ++kc) {

@@ -209,15 +209,20 @@ __global__ void conv3x3_direct_kernel(const TI* __restrict__ in, int in_nchw,
 // conv_in-type: tiny Cin (<= 8), many output channels.  Weights are staged once per block in shared
 // memory transposed to [tap*Cin + c][Cout] so that consecutive threads (consecutive co) read
 // consecutive words; each block produces PIX pixels x Cout outputs with coalesced stores.
-constexpr int SC_PIX = 32;
+constexpr int SC_PIX = 128;  // pixels per block
+// conv_in-type: tiny Cin (<= 8), many output channels, NHWC output.  FMA-bound when register-blocked: a thread
+// owns 4 pixels x 8 channels (channels c4..c4+3 and Cout/2 + c4..c4+3 so that both weight loads of a warp are
+// conflict-free float4 rows); weights [k][Cout] and the 128-pixel patch matrix [k][pixel] sit in shared memory,
+// so every FMA costs 3/32 of a 16-byte shared load (the first version did 2 scalar loads per FMA: LDS-bound, and
+// re-staged the 46 KB weight matrix for every 32 pixels).  Requires Cout % 8 == 0.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 conv3x3_small_cin_kernel(const TI* __restrict__ in, int in_nchw, const float* __restrict__ w,
                          const float* __restrict__ bias, TO* __restrict__ out, int n_img, int H, int W,
                          int Cin, int Cout, int out_H, int out_row_off) {
-  extern __shared__ float ws[];  // [9*Cin][Cout] weights, then [SC_PIX][9*Cin] input patches
-  float* xs = ws + 9 * Cin * Cout;
+  extern __shared__ __align__(16) float ws[];  // [9*Cin][Cout] weights, then [9*Cin][SC_PIX] input patches
   const int kk = 9 * Cin;
+  float* xs = ws + kk * Cout;
   for (int i = threadIdx.x; i < kk * Cout; i += 256) {
     int co = i / kk, k = i - co * kk;  // source order [co][tap][c]
     ws[k * Cout + co] = w[i];
@@ -225,7 +230,7 @@ conv3x3_small_cin_kernel(const TI* __restrict__ in, int in_nchw, const float* __
   const long long pix0 = blockIdx.x * static_cast<long long>(SC_PIX);
   const long long npix = static_cast<long long>(n_img) * H * W;
   for (int i = threadIdx.x; i < SC_PIX * kk; i += 256) {
-    int pp = i / kk, k = i - pp * kk;
+    int k = i / SC_PIX, pp = i - k * SC_PIX;  // consecutive threads -> consecutive pixels (coalesced for NCHW input)
     long long pix = pix0 + pp;
     float v = 0.f;
     if (pix < npix) {
@@ -236,19 +241,45 @@ conv3x3_small_cin_kernel(const TI* __restrict__ in, int in_nchw, const float* __
       if (yy >= 0 && yy < H && xx >= 0 && xx < W)
         v = in_nchw ? ld_f(in + ((n * Cin + c) * H + yy) * W + xx) : ld_f(in + ((n * H + yy) * W + xx) * Cin + c);
     }
-    xs[i] = v;
+    xs[k * SC_PIX + pp] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < SC_PIX * Cout; i += 256) {
-    int pp = i / Cout, co = i - pp * Cout;
-    long long pix = pix0 + pp;
-    if (pix >= npix) break;
-    float acc = bias ? bias[co] : 0.f;
-    const float* xr = xs + pp * kk;
-    for (int k = 0; k < kk; ++k) acc = fmaf(xr[k], ws[k * Cout + co], acc);
-    int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
-    long long n = pix / (static_cast<long long>(W) * H);
-    st_f(out + ((n * out_H + out_row_off + y) * W + x) * Cout + co, acc);
+  const int half = Cout >> 1;
+  const int ncg = half >> 2;                 // channel groups: 4 + 4 channels each
+  const int ntile = (SC_PIX / 4) * ncg;      // thread tiles of 4 pixels x 8 channels
+  for (int t = threadIdx.x; t < ntile; t += 256) {
+    const int cg = t % ncg, pg = t / ncg;    // consecutive lanes -> consecutive channel groups of one pixel group
+    const int c0 = cg * 4, c1 = half + cg * 4, p0 = pg * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+    for (int k = 0; k < kk; ++k) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + k * SC_PIX + p0);
+      const float4 wa = *reinterpret_cast<const float4*>(ws + k * Cout + c0);
+      const float4 wb = *reinterpret_cast<const float4*>(ws + k * Cout + c1);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        acc[p][0] = fmaf(xa[p], wa.x, acc[p][0]); acc[p][1] = fmaf(xa[p], wa.y, acc[p][1]);
+        acc[p][2] = fmaf(xa[p], wa.z, acc[p][2]); acc[p][3] = fmaf(xa[p], wa.w, acc[p][3]);
+        acc[p][4] = fmaf(xa[p], wb.x, acc[p][4]); acc[p][5] = fmaf(xa[p], wb.y, acc[p][5]);
+        acc[p][6] = fmaf(xa[p], wb.z, acc[p][6]); acc[p][7] = fmaf(xa[p], wb.w, acc[p][7]);
+      }
+    }
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    if (bias) { ba = *reinterpret_cast<const float4*>(bias + c0); bb = *reinterpret_cast<const float4*>(bias + c1); }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const long long pix = pix0 + p0 + p;
+      if (pix >= npix) break;
+      int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+      long long n = pix / (static_cast<long long>(W) * H);
+      TO* o = out + ((n * out_H + out_row_off + y) * W + x) * Cout;
+      st4(o + c0, make_float4(acc[p][0] + ba.x, acc[p][1] + ba.y, acc[p][2] + ba.z, acc[p][3] + ba.w));
+      st4(o + c1, make_float4(acc[p][4] + bb.x, acc[p][5] + bb.y, acc[p][6] + bb.z, acc[p][7] + bb.w));
+    }
   }
 }
 
@@ -494,7 +525,9 @@ extern "C" int iir_conv3x3_direct(const void* in, int in_dtype, int in_nchw, con
     count_launch();
     return check_launch("iir_conv3x3_direct");
   }
-  if (!out_nchw && Cin <= 8 && (size_t)(9 * Cin) * (Cout + SC_PIX) * sizeof(float) <= 200 * 1024) {
+  if (!out_nchw && Cin <= 8 && Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+      (size_t)(9 * Cin) * (Cout + SC_PIX) * sizeof(float) <= 200 * 1024) {
     size_t smem = (size_t)(9 * Cin) * (Cout + SC_PIX) * sizeof(float);
     long long npix = static_cast<long long>(n_img) * H * W;
     int blocksp = static_cast<int>((npix + SC_PIX - 1) / SC_PIX);

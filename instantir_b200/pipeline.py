@@ -258,7 +258,7 @@ class InstantIRPipeline:
                     with torch.cuda.stream(S.side):
                         state = unet.forward_down_mid(x_in, t_dev, prompt_all, added_cond_kwargs=added)
                     down, mid = agg(image_all, t_dev, encoder_hidden_states=prompt_all, controlnet_cond=cond,
-                                    added_cond_kwargs=agg_added, return_dict=False)
+                                    added_cond_kwargs=agg_added, return_dict=False, head_stream=S.side)
                     cur.wait_stream(S.side)
                     eps = unet.forward_up(state, down, mid, cond_scale)[0]
                     return eps, down, mid

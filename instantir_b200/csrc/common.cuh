@@ -172,6 +172,21 @@ __device__ __forceinline__ float gelu_erf_f(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
 
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): one rcp + one ex2 + a degree-5 Horner chain instead of
+// erff's ~35 branchy instructions; used by the 16-bit tensor-core epilogues only (the fp32 check mode keeps erff)
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = 1.0f - p * ex2_approx(-x * x * 1.4426950408889634f);  // erf(|v|/sqrt2)
+  return 0.5f * v + 0.5f * fabsf(v) * e;                                // 0.5 v (1 + sign(v) e)
+}
+
 // ---- Programmatic Dependent Launch ---------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -115,7 +115,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(full_bar) + 256;  // 8 epilogue warps x EPI_STAGE_BYTES
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // 2 x 256 floats (tile bias)
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(s_bias) + 2048;  // 8 epilogue warps x slots x EPI_STAGE_BYTES
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -282,6 +283,14 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       long long mrow[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mrow[i] = row_to_m(lane_base + i * 4 + crow);
+      // the tile's bias vector goes through shared memory once (each row-phase thread needs all of it: 8-16
+      // broadcast global loads per chunk before); double-buffered by tile parity, one named barrier per tile
+      float* sb = s_bias + (acc_i & 1) * 256;
+      if (p.bias) {
+        const int t = threadIdx.x - 64;  // 0..255 over the 8 epilogue warps
+        if (t < p.BN) sb[t] = (c.n0 + t < p.N) ? p.bias[c.n0 + t] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 
       const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
       const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
@@ -322,10 +331,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (pn + j < p.N) {
-              float4 b = ld4(p.bias + pn + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
+            float4 b = *reinterpret_cast<const float4*>(sb + cc + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
         if (p.rowvec) {
@@ -340,10 +347,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         }
         if (p.act == IIR_ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
         } else if (p.act == IIR_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         }
         if (PAIR) {
           float g[32];
@@ -352,15 +359,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (pn + half + j < p.N) {
-                float4 b = ld4(p.bias + pn + half + j);
-                g[j] += b.x; g[j + 1] += b.y; g[j + 2] += b.z; g[j + 3] += b.w;
-              }
+              float4 b = *reinterpret_cast<const float4*>(sb + half + cc + j);
+              g[j] += b.x; g[j + 1] += b.y; g[j + 2] += b.z; g[j + 3] += b.w;
             }
           }
           if (PAIR == IIR_PAIR_GEGLU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_fast(g[j]);
           } else {  // SFT: h * (gamma + 1) + beta
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -574,15 +579,15 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     if (slots > 3) slots = 3;
     int want = mma2 ? 6 : 4;
     if (want > p.num_kb + 1) want = p.num_kb + 1;
-    while (slots > 1 && (227 * 1024 - 1024 - 256 - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
+    while (slots > 1 && (227 * 1024 - 1024 - 256 - 2048 - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
   }
   p.epi_slots = slots;
   const int epi_bytes = 8 * slots * EPI_STAGE_BYTES;
-  int stages = (227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
+  int stages = (227 * 1024 - 1024 - 256 - 2048 - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 2048 + epi_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
 
   const int num_tiles = p.tiles_m_cl * p.tiles_n;  // super-tiles, one per cluster at a time

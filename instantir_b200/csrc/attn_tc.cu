@@ -319,7 +319,15 @@ constexpr int ATS_KV_STAGES = 3;
 // 64 keys).  Block j is segment j with its own K/V tensors; its softmax is complete after that block, so P is
 // normalised (and weighted by seg_scale) in registers and both segments accumulate straight into the same O:
 //   out = sum_s seg_scale[s] * softmax(Q K_s^T) V_s     with no per-segment accumulator and no final rescale.
-template <bool PERBLOCK>
+// element j of a row: SFU exp2, or the FMA-pipe polynomial for every POLY-th element
+template <int POLY>
+__device__ __forceinline__ float exp2_sel(int j, float x) {
+  if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) return ex2_poly(x);
+  return ex2_approx(x);
+}
+
+// POLY = n > 0: every n-th exponential of a row is computed on the FMA pipe (ex2_poly) instead of the SFU.
+template <bool PERBLOCK, int POLY>
 __global__ void __launch_bounds__(ATS_THREADS, 2)
 attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -531,16 +539,16 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       uint32_t pk0[16], pk1[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(sr[j]), sl2, mneg));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), sl2, mneg));
+        const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[j]), sl2, mneg));
+        const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[j + 1]), sl2, mneg));
         sums[j & 7] += e0;
         sums[(j + 1) & 7] += e1;
         pk0[j >> 1] = pack_bf16(e0, e1);
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(sr[32 + j]), sl2, mneg));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(sr[32 + j + 1]), sl2, mneg));
+        const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[32 + j]), sl2, mneg));
+        const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[32 + j + 1]), sl2, mneg));
         sums[j & 7] += e0;
         sums[(j + 1) & 7] += e1;
         pk1[j >> 1] = pack_bf16(e0, e1);
@@ -574,8 +582,8 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[g * 32 + j]), sl2, mneg));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[g * 32 + j + 1]), sl2, mneg));
+          const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[g * 32 + j]), sl2, mneg));
+          const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[g * 32 + j + 1]), sl2, mneg));
           sums[j & 7] += e0;
           sums[(j + 1) & 7] += e1;
           pk[j >> 1] = pack_bf16(e0, e1);
@@ -684,12 +692,24 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
     v1 = (ev && ev[0] == '1') ? 1 : 0;
   }
   const bool one_block_each = a->n_seg == 2 && a->kv_len[0] <= 128 && a->kv_len[1] <= 128;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* ev = getenv("IIR_ATTN_POLY");  // 0 = all exponentials on the SFU; n = every n-th on the FMA pipe
+    poly = ev ? atoi(ev) : 4;
+  }
+#define ATS_LAUNCH(PB, PL)                                                                                         \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(attn_ts_kernel<PB, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<PB, PL>, grid, dim3(ATS_THREADS), smem, st, p);            \
+  } while (0)
   if (a->n_seg == 1 && !v1) {
-    e = cudaFuncSetAttribute(attn_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<false>, grid, dim3(ATS_THREADS), smem, st, p);
+    if (poly == 2) ATS_LAUNCH(false, 2);
+    else if (poly == 3) ATS_LAUNCH(false, 3);
+    else if (poly == 4) ATS_LAUNCH(false, 4);
+    else if (poly == 8) ATS_LAUNCH(false, 8);
+    else ATS_LAUNCH(false, 0);
   } else if (one_block_each && !v1) {
-    e = cudaFuncSetAttribute(attn_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<true>, grid, dim3(ATS_THREADS), smem, st, p);
+    ATS_LAUNCH(true, 0);
   } else if (a->n_seg == 1) {
     e = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = launch_pdl(attn_tc_kernel<1>, grid, dim3(ATT_THREADS), smem, st, p);

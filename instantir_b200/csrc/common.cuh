@@ -163,6 +163,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x WITHOUT the SFU: round-to-nearest split x = n + f (magic-number add), degree-3 near-minimax polynomial for
+// 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 16-bit rounding of P), exponent patched in with one
+// integer add.  8 FMA/ALU-pipe instructions that run beside MUFU.EX2: the attention softmax is bound by the 16
+// exp2/clk/SM of the SFU, so a fraction of its exponentials is computed this way (the FlashAttention-4 trick).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(f, 0.055171653628349304f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 // same with the approximate divide (2 ulp): the IEEE divide above costs ~4x the instructions, which made
 // the GroupNorm+SiLU pass issue-bound instead of memory-bound

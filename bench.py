@@ -33,7 +33,10 @@ sys.path.insert(0, ROOT)
 
 STEPS_PER_IMAGE = 30
 # algorithmic FLOPs per image-step at 1024², both CFG branches (SURVEY.md §8d / BASELINE.md §2)
-FLOPS_STEP = {"config2": 25.89e12, "config3": 39.36e12}
+FLOPS_STEP = {"config2": 25.89e12, "config3": 39.36e12,
+              # config 4: 18 previewing steps + 12 UNet-only steps (control_guidance_end=0.6): 870.1 T per image;
+              # config 5: 2048² with previewer, 6764 T per image
+              "config4": 870.1e12 / 30, "config5": 6764e12 / 30}
 FLOPS_UNET_BRANCH = {128: 6.737e12, 64: None, 32: 0.378e12}
 
 
@@ -230,15 +233,16 @@ def run_ours(args):
 
     wl = args.workload
     cfg = pcfg.tiny() if wl == "config1" else pcfg.sdxl()
-    latent = 32 if wl == "config1" else 128
-    preview = wl == "config3"
+    latent = {"config1": 32, "config5": 256}.get(wl, 128)
+    preview = wl in ("config3", "config4", "config5")
     B = args.batch
     unet, agg = build_models(cfg, dev, args.precision, with_lora=preview)
     pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
     cfgp = parallel.CFGParallel() if (args.cfg_parallel and world > 1) else None
     host = host_inputs(cfg, B, latent, seed=1234 + (rank // 2 if cfgp else rank))
     call_kw = dict(num_inference_steps=STEPS_PER_IMAGE, guidance_scale=7.0, previewer_scheduler=LCMSingleStepScheduler(),
-                   preview_start=0.0 if preview else 1.0, cfg_parallel=cfgp, use_cuda_graph=True)
+                   preview_start=0.0 if preview else 1.0, cfg_parallel=cfgp, use_cuda_graph=True,
+                   control_guidance_end=0.6 if wl == "config4" else 1.0, agg_ahead=args.agg_ahead)
 
     # ---- device-resident leg: inputs already in HBM, K steps timed with CUDA events
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -309,7 +313,9 @@ def run_ours(args):
         if cfgp is None:
             pipe2 = InstantIRPipeline(unet, agg, DDPMScheduler())   # fresh graph cache: captured with the hooks on
             ops.PROFILE = []
-            loop2 = pipe2(**devin, generator=gen, prepare_only=True, **call_kw)
+            # single stream for this leg: with the aggregator || UNet fork two kernels share the SMs and every
+            # per-launch duration would include its neighbour's
+            loop2 = pipe2(**devin, generator=gen, prepare_only=True, overlap_streams=False, **call_kw)
             loop2.step(0)                    # eager warm-up + capture (+ first replay)
             captured = list(ops.PROFILE)
             ops.PROFILE = None
@@ -327,7 +333,8 @@ def run_ours(args):
                 d["flops"] += work.get("flops", 0.0)
                 d["bytes"] += work.get("bytes", 0.0)
             ops.PROFILE = None
-            del loop2, pipe2
+            del pipe2
+            loop2 = None
             tc = {"launches": 0, "ms": 0.0, "flops": 0.0}
             for k in ("gemm_tc", "conv3x3_tc"):
                 if k in breakdown:
@@ -344,19 +351,22 @@ def run_ours(args):
                         "traffic": 28.4e6,
                         "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                         "launches_per_step": tc["launches"], "ms_per_step": tc["ms"],
-                        "timing": "CUDA event-record nodes around every launch inside the replayed CUDA graphs",
+                        "timing": "CUDA event-record nodes around every launch inside the replayed CUDA graphs, captured on ONE stream (the timed step overlaps aggregator and UNet down path on two)",
                         "flops_per_launch_avg": tc["flops"] / tc["launches"]}
             for d in breakdown.values():
                 d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] and d["flops"] else None
                 d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] and d["bytes"] else None
         step_flops = FLOPS_STEP.get(wl)
         line = {
-            "metric": "1024x1024 restored images per second (30 steps, CFG 7)" if wl != "config1" else "256x256 restored images per second (30-step schedule, CFG 7)",
+            "metric": {"config1": "256x256 restored images per second (30-step schedule, CFG 7)",
+                       "config5": "2048x2048 restored images per second (30 steps, CFG 7)"}.get(wl, "1024x1024 restored images per second (30 steps, CFG 7)"),
             "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": {"config2": "BASELINE configs[1]: full SDXL UNet + InstantIR aggregator + IP-adapter, random-init, 1024² (latent 128²), 30-step DDPM schedule, CFG 7, previewer off",
                                     "config3": "BASELINE configs[2]: config 2 + LCM previewer every step (preview_start=0)",
+                                    "config4": "BASELINE configs[3]: previewer on, creative_start (control_guidance_end) = 0.6: 18 full steps + 12 UNet-only steps per image",
+                                    "config5": "BASELINE configs[4]: 2048² (latent 256²), previewer on",
                                     "config1": "BASELINE configs[0]: scaled-down step, 256²"}[wl],
                        "images_per_rank": B, "parallelism": ("cfg-parallel pairs x dp" if cfgp else f"dp{world}"),
                        "step": "aggregator fwd + UNet fwd (2 CFG branches) + fused CFG/DDPM" + (" + previewer UNet fwd + LCM" if preview else ""),
@@ -375,7 +385,7 @@ def run_ours(args):
         if world == 1 and args.precision == "bf16" and not args.no_fp16:
             # the same step with IEEE-fp16 operands (the reference's own precision; meets the 1e-2 parity bar)
             try:
-                del loop, loop2, pipe, unet, agg
+                del loop, pipe, unet, agg
                 torch.cuda.empty_cache()
                 u16, a16 = build_models(cfg, dev, "fp16", with_lora=preview)
                 p16 = InstantIRPipeline(u16, a16, DDPMScheduler())
@@ -437,11 +447,12 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--batch", type=int, default=1, help="images per rank")
     ap.add_argument("--cfg-parallel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fp16", action="store_true", help="skip the fp16 comparison leg")
+    ap.add_argument("--agg-ahead", action="store_true", help="run Aggregator(t_{i+1}) beside the whole UNet(t_i) (previewer-off workloads)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="16-bit operand type of the timed run")
     args = ap.parse_args()
     if args.warmup < 3:

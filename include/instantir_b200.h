@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 3
+#define IIR_ABI_VERSION 4
 
 typedef enum {
   IIR_OK = 0,
@@ -83,6 +83,24 @@ typedef struct {
                            256 x bn tile, each CTA stages half of the weight tile)         */
   int64_t ld_rowvec;    /* row stride of rowvec in floats (0 = N): lets rowvec be a column slice
                            of the banked time-embedding projections (iir_linear_small)    */
+  /* ---- LayerNorm folded into the GEMMs around it (tc only; nn.LayerNorm of BasicTransformerBlock,
+   * module/min_sdxl.py:546-556).  LN(x)·Wᵀ + b = rstd_m·(x·W'ᵀ − mean_m·colsum(W')) + b' with W' = W∘gamma,
+   * b' = W·beta + b, so the GEMM that WRITES the fp32 stream x also emits a 16-bit copy of it and per-row
+   * partial (sum, sum of squares), and the GEMM that CONSUMES LN(x) reads that copy and applies mean / rstd in
+   * its epilogue: no LayerNorm launch, no extra pass over x.
+   * producer: ln_stats_out [M, 2] int64 fixed-point accumulators (sum * 2^32, sum of squares * 2^24) that every N
+   *           tile ADDS its rows' partial sums into (integer atomics: order-independent, so results stay
+   *           bit-reproducible); must be zero on entry.  ln_out16 [M, N] = 16-bit copy of `out` (optional).
+   *           Needs pair == NONE, residual NULL or fp32.
+   * consumer: ln_stats_in (the producer's accumulators), ln_colsum [N] = sum_k W'[n,k] (packed order), ln_eps; the
+   *           row mean uses K as the LN width.  ln_stats_zero (optional) [M, 2] int64 is cleared for the NEXT
+   *           producer (two accumulators alternate along a chain of producer / consumer GEMMs).               */
+  void* ln_stats_out;
+  void* ln_out16; int64_t ld_ln_out16;
+  const void* ln_stats_in;
+  void* ln_stats_zero;
+  const float* ln_colsum;
+  float ln_eps;
 } iir_gemm_args;
 
 /* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
@@ -46,6 +46,8 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("ld_out", C.c_int64),
         ("act", C.c_int), ("pair", C.c_int), ("bn", C.c_int), ("cluster", C.c_int),
         ("ld_rowvec", C.c_int64),
+        ("ln_stats_out", C.c_void_p), ("ln_out16", C.c_void_p), ("ld_ln_out16", C.c_int64),
+        ("ln_stats_in", C.c_void_p), ("ln_stats_zero", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
     ]
 
 

@@ -36,8 +36,9 @@ class SFTHead:
         self.b_ga = _pack_pairs(src.get(p + ".0.mul.bias"), src.get(p + ".0.add.bias"), self.bn).contiguous()
         self.zero_conv = Linear(rt, _ShortcutSrc(src), p + ".1")
 
-    def __call__(self, canvas: FMap) -> torch.Tensor:
-        """canvas [n, 2H, W, C] fp32 -> residual [n, C, H, W] view (NHWC memory, activation dtype)."""
+    def __call__(self, canvas: FMap, out=None) -> torch.Tensor:
+        """canvas [n, 2H, W, C] fp32 -> residual [n, C, H, W] view (NHWC memory, activation dtype), written into the
+        caller's [n*H*W, C] buffer `out` when given."""
         rt, C = self.rt, self.C
         n, H, W = canvas.n, canvas.H // 2, canvas.W
         M, half = n * H * W, H * W * C
@@ -49,7 +50,7 @@ class SFTHead:
         sft = rt.empty(M, C)
         ops.gemm(actv.t, self.w_ga, sft, M=M, N=2 * C, K=9 * self.hidden, bias=self.b_ga, pair=ops.PAIR_SFT, aux=h,
                  bn=self.bn, conv=dict(n_img=n, H=H, W=W, Cin=self.hidden), tc=rt.tc)
-        out = self.zero_conv(sft, M)
+        out = self.zero_conv(sft, M, out=out)
         return FMap(out, n, H, W, C).nchw()
 
 
@@ -93,10 +94,13 @@ class Aggregator(_EmbeddingMixin):
 
     def forward(self, sample, timestep, encoder_hidden_states=None, controlnet_cond=None, cat_dim=-2,
                 conditioning_scale=1.0, class_labels=None, timestep_cond=None, attention_mask=None,
-                added_cond_kwargs=None, cross_attention_kwargs=None, return_dict=False, head_stream=None):
-        """`head_stream` (extension): the SFT heads of every down block but the last are enqueued on that stream as
+                added_cond_kwargs=None, cross_attention_kwargs=None, return_dict=False, head_stream=None,
+                out_buffers=None):
+        """Extensions.  `head_stream`: the SFT heads of every down block but the last are enqueued on that stream as
         soon as the block's skip tensors exist, so they overlap the rest of the trunk; the CALLER joins
-        `head_stream` before reading the returned residuals."""
+        `head_stream` before reading the returned residuals.  `out_buffers` = (list of 9 [M_i, C_i] tensors, [M, C]
+        tensor): the heads write the residuals there (the pipeline ping-pongs two such sets to run the aggregator
+        of the NEXT step beside the UNet of the current one)."""
         if self.config.controlnet_conditioning_channel_order != "rgb":
             raise ValueError(f"unknown `controlnet_conditioning_channel_order`: {self.config.controlnet_conditioning_channel_order}")
         if cat_dim not in (-2, 2):
@@ -119,6 +123,7 @@ class Aggregator(_EmbeddingMixin):
         skips = [x]
         kw = dict(cross_attention_kwargs or {})
         down = [None] * len(self.controlnet_down_blocks)
+        ob_down, ob_mid = out_buffers if out_buffers is not None else ([None] * len(down), None)
         done = 0
         for bi, blk in enumerate(self.down_blocks):
             x, outs = blk(x, temb_act, None, kw)
@@ -129,12 +134,12 @@ class Aggregator(_EmbeddingMixin):
                 head_stream.wait_event(ev)
                 with torch.cuda.stream(head_stream):
                     for i in range(done, len(skips)):
-                        down[i] = self.controlnet_down_blocks[i](skips[i])
+                        down[i] = self.controlnet_down_blocks[i](skips[i], ob_down[i])
                 done = len(skips)
         x = self.mid_block(x, temb_act, None, kw)
         for i in range(done, len(skips)):
-            down[i] = self.controlnet_down_blocks[i](skips[i])
-        mid = self.controlnet_mid_block(x)
+            down[i] = self.controlnet_down_blocks[i](skips[i], ob_down[i])
+        mid = self.controlnet_mid_block(x, ob_mid)
         if not return_dict:
             return (down, mid)
         return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)

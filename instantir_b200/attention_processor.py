@@ -18,7 +18,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .nn import Linear, Runtime, SmallLinear, _Packed, _bias, _load_w
+from .nn import Linear, LNStream, Runtime, SmallLinear, _Packed, _bias, _load_w
 
 HEAD_DIM = 64
 SOFTMAX_SCALE = HEAD_DIM ** -0.5
@@ -69,19 +69,33 @@ def silu_of(rt: Runtime, temb: torch.Tensor) -> torch.Tensor:
 class _Fused:
     """several bias-free nn.Linear weights stacked along N (fused QKV / KV projections)."""
 
-    def __init__(self, rt, src, names):
-        parts = [_load_w(rt, src, n) for n in names]
-        base = torch.cat([p.base for p in parts], 0).contiguous()
-        lora = None
-        if any(p.lora is not None for p in parts):
-            lora = torch.cat([p.lora if p.lora is not None else p.base for p in parts], 0).contiguous()
-        self.rt, self.w = rt, _Packed(rt, base, lora)
-        self.N, self.K = base.shape
+    def __init__(self, rt, src, names, fold=None):
+        parts = [_load_w(rt, src, n, fold=fold) for n in names]
+        any_lora = any(p.lora is not None for p in parts)
+
+        def cat(get):
+            base = torch.cat([get(p).base for p in parts], 0).contiguous()
+            lora = None
+            if any_lora:
+                lora = torch.cat([get(p).lora if get(p).lora is not None else get(p).base for p in parts], 0).contiguous()
+            return _Packed(rt, base, lora)
+
+        self.rt, self.w = rt, cat(lambda p: p)
+        self.folded = fold is not None
+        if self.folded:
+            self.colsum, self.bias = cat(lambda p: p.colsum), cat(lambda p: p.bias)
+        self.N, self.K = self.w.base.shape
 
     def __call__(self, a, M, out=None, out_dtype=None):
         if out is None:
             out = torch.empty(M, self.N, device=self.rt.device, dtype=out_dtype or self.rt.act_dtype)
-        ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, tc=self.rt.tc)
+        if isinstance(a, LNStream) != self.folded:
+            raise ops._lib.IIRError("a LayerNorm-folded projection takes the LNStream of its transformer block (and only it)")
+        if self.folded:
+            ops.gemm(a.h16, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.bias.get(), tc=True,
+                     ln_in=(a, self.colsum.get(), a.eps))
+        else:
+            ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, tc=self.rt.tc)
         return out
 
 
@@ -89,12 +103,14 @@ class Attention:
     """diffusers Attention as configured for SDXL (q/k/v no bias, out bias, head_dim 64) exposing
     the fields the reference processors read (.to_q/.to_k/.to_v/.to_out/.heads/...)."""
 
-    def __init__(self, rt: Runtime, src, p: str, C: int, heads: int, cross_dim: Optional[int] = None):
+    def __init__(self, rt: Runtime, src, p: str, C: int, heads: int, cross_dim: Optional[int] = None, fold=None):
+        """fold = (gamma, beta) of the block's LayerNorm in front of this attention: its query-side projection
+        then takes the block's LNStream instead of a normalised tensor (nn.LNStream)."""
         self.rt, self.C, self.heads, self.cross_dim = rt, C, heads, cross_dim
         if cross_dim is None:
-            self.to_qkv = _Fused(rt, src, [p + ".to_q", p + ".to_k", p + ".to_v"])
+            self.to_qkv = _Fused(rt, src, [p + ".to_q", p + ".to_k", p + ".to_v"], fold=fold)
         else:
-            self.to_q = Linear(rt, src, p + ".to_q", bias=False)
+            self.to_q = Linear(rt, src, p + ".to_q", bias=False, fold=fold)
             self.to_kv = _Fused(rt, src, [p + ".to_k", p + ".to_v"])
         self.to_out = [Linear(rt, src, p + ".to_out.0"), None]
         self.processor = AttnProcessor2_0()
@@ -115,6 +131,8 @@ class Attention:
 
     # -- helpers shared by the processors
     def _to_act(self, x3d):
+        if isinstance(x3d, LNStream):
+            return x3d
         B, n, C = x3d.shape
         x = x3d.reshape(B * n, C)
         if x.dtype != self.rt.act_dtype or not x.is_contiguous():
@@ -128,6 +146,9 @@ class Attention:
         return self.ctx.get("text_kv", text, lambda out: self.to_kv(self._to_act(text), B * nt, out=out))
 
     def project_out(self, o, M, residual):
+        if isinstance(residual, LNStream):  # in place on the fp32 stream; refreshes its 16-bit copy + row statistics
+            self.to_out[0](o, M, out=residual.h, residual=residual.h, ln_out=residual)
+            return residual.h
         if residual is not None:
             r2 = residual.reshape(M, self.C)
             return self.to_out[0](o, M, out=r2, residual=r2)

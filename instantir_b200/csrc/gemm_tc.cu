@@ -47,6 +47,9 @@ constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 columns, XOR-swizzled
+constexpr int VEC_BYTES = 4096;        // tile bias + tile column sums, 2 x 256 floats each (double-buffered)
+constexpr float LN_S1_SCALE = 4294967296.f;  // 2^32: |row sum| < 2^31
+constexpr float LN_S2_SCALE = 16777216.f;    // 2^24: row sum of squares < 2^39
 
 struct alignas(64) GemmTcParams {
   CUtensorMap tmA;
@@ -71,6 +74,14 @@ struct alignas(64) GemmTcParams {
   int out_bf16;
   long long ld_out;
   int act;
+  // LayerNorm folded into the GEMMs around it
+  long long* ln_stats_out;        // producer: per-row fixed-point (sum, sum of squares) of the final fp32 values
+  void* ln_out16;                 // producer: 16-bit copy of the output (the consumer's A operand)
+  long long ld_ln16;
+  const long long* ln_stats_in;   // consumer: the producer's row sums
+  long long* ln_stats_zero;       // consumer: accumulator to clear for the next producer
+  const float* ln_colsum;         // consumer: sum_k W'[n, k]
+  float ln_inv_k, ln_eps;
 };
 
 struct TileCoord {
@@ -116,7 +127,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // 2 x 256 floats (tile bias)
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(s_bias) + 2048;  // 8 epilogue warps x slots x EPI_STAGE_BYTES
+  float* s_cs = s_bias + 512;                                                             // 2 x 256 floats (tile column sums)
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(s_bias) + VEC_BYTES;  // 8 epilogue warps x slots x EPI_STAGE_BYTES
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,11 +298,29 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       // the tile's bias vector goes through shared memory once (each row-phase thread needs all of it: 8-16
       // broadcast global loads per chunk before); double-buffered by tile parity, one named barrier per tile
       float* sb = s_bias + (acc_i & 1) * 256;
-      if (p.bias) {
+      float* sc = s_cs + (acc_i & 1) * 256;
+      if (p.bias || p.ln_colsum) {
         const int t = threadIdx.x - 64;  // 0..255 over the 8 epilogue warps
-        if (t < p.BN) sb[t] = (c.n0 + t < p.N) ? p.bias[c.n0 + t] : 0.f;
+        if (t < p.BN) {
+          if (p.bias) sb[t] = (c.n0 + t < p.N) ? p.bias[c.n0 + t] : 0.f;
+          if (p.ln_colsum) sc[t] = (c.n0 + t < p.N) ? p.ln_colsum[c.n0 + t] : 0.f;
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      // folded LayerNorm, consumer side: y = rstd * (x W'^T) - rstd * mean * colsum(W') + b'  (b' arrives as bias);
+      // mean / rstd of this thread's row from the producer's partial sums
+      float ln_rstd = 1.f, ln_nm = 0.f;
+      if (p.ln_stats_in && valid) {
+        const longlong2 t = *reinterpret_cast<const longlong2*>(p.ln_stats_in + m_own * 2);
+        const float mean = __ll2float_rn(t.x) * (1.0f / LN_S1_SCALE) * p.ln_inv_k;
+        const float var = fmaxf(__ll2float_rn(t.y) * (1.0f / LN_S2_SCALE) * p.ln_inv_k - mean * mean, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nm = -mean * ln_rstd;
+        // the accumulator the NEXT producer will add into is cleared here, by the tile that owns column 0 of the row
+        if (p.ln_stats_zero && c.n0 == 0 && chunk_par == 0)
+          *reinterpret_cast<longlong2*>(p.ln_stats_zero + m_own * 2) = make_longlong2(0, 0);
+      }
+      float ln_s1 = 0.f, ln_s2 = 0.f;  // producer side: this thread's row, this warp's chunks
 
       const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
       const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
@@ -328,7 +358,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int on = nout0 + cc;  // output column of v[0]
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+        if (p.ln_stats_in) {  // rstd * acc + (-mean * rstd) * colsum + b'  (b' is always present on this path)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+            const float4 b = *reinterpret_cast<const float4*>(sb + cc + j);
+            v[j] = fmaf(ln_rstd, v[j], fmaf(ln_nm, s4.x, b.x)); v[j + 1] = fmaf(ln_rstd, v[j + 1], fmaf(ln_nm, s4.y, b.y));
+            v[j + 2] = fmaf(ln_rstd, v[j + 2], fmaf(ln_nm, s4.z, b.z)); v[j + 3] = fmaf(ln_rstd, v[j + 3], fmaf(ln_nm, s4.w, b.w));
+          }
+        } else if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b = *reinterpret_cast<const float4*>(sb + cc + j);
@@ -356,7 +394,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           float g[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r2[j]);
-          if (p.bias) {
+          if (p.ln_stats_in) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sc + half + cc + j);
+              const float4 b = *reinterpret_cast<const float4*>(sb + half + cc + j);
+              g[j] = fmaf(ln_rstd, g[j], fmaf(ln_nm, s4.x, b.x)); g[j + 1] = fmaf(ln_rstd, g[j + 1], fmaf(ln_nm, s4.y, b.y));
+              g[j + 2] = fmaf(ln_rstd, g[j + 2], fmaf(ln_nm, s4.z, b.z)); g[j + 3] = fmaf(ln_rstd, g[j + 3], fmaf(ln_nm, s4.w, b.w));
+            }
+          } else if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b = *reinterpret_cast<const float4*>(sb + half + cc + j);
@@ -397,12 +443,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             float4 q = *a4;
             q.x += v[4 * c4]; q.y += v[4 * c4 + 1]; q.z += v[4 * c4 + 2]; q.w += v[4 * c4 + 3];
             *a4 = q;
+            if (p.ln_stats_out && on + 4 * c4 < n_out_total) {  // columns past N hold stale staging data
+              ln_s1 += (q.x + q.y) + (q.z + q.w);
+              ln_s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+            }
           }
         } else {
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            *reinterpret_cast<float4*>(slot + lane * 128 + ((c4 ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 q = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            *reinterpret_cast<float4*>(slot + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = q;
+            if (p.ln_stats_out && on + 4 * c4 < n_out_total) {
+              ln_s1 += (q.x + q.y) + (q.z + q.w);
+              ln_s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+            }
+          }
         }
         __syncwarp();
         const int ocol = on + cc4 * 4;
@@ -421,10 +476,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
             if (p.out_bf16) st4(reinterpret_cast<h16*>(p.out) + m * p.ld_out + ocol, x);
             else st4(reinterpret_cast<float*>(p.out) + m * p.ld_out + ocol, x);
+            if (p.ln_out16) st4(reinterpret_cast<h16*>(p.ln_out16) + m * p.ld_ln16 + ocol, x);
           }
         }
         __syncwarp();
         if (pre && kc + R < nchunks_w) prefetch(kc + R);
+      }
+      if (p.ln_stats_out && valid) {
+        // fixed-point accumulation: integer adds commute, so the row sums do not depend on the order in which
+        // the N tiles (and the two warps of a lane quarter) arrive — results stay run-to-run bit-identical
+        unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.ln_stats_out) + m_own * 2;
+        atomicAdd(acc, static_cast<unsigned long long>(__float2ll_rn(ln_s1 * LN_S1_SCALE)));
+        atomicAdd(acc + 1, static_cast<unsigned long long>(__float2ll_rn(ln_s2 * LN_S2_SCALE)));
       }
       tc_fence_before();
       if (MMA2 && rank != 0) mbar_arrive_remote(&tempty_bar[buf], 0);  // the leader's MMA thread waits for both
@@ -567,6 +630,28 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;
   p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act;
+  if (a->ln_stats_out) {
+    IIR_REQUIRE(a->pair == IIR_PAIR_NONE && (!a->residual || a->res_dtype == IIR_F32) && !a->conv,
+                "iir_gemm_tc: ln_stats_out needs a plain linear epilogue with no or an fp32 residual");
+    IIR_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats_out) & 15) == 0, "iir_gemm_tc: ln_stats_out must be 16-byte aligned");
+    IIR_REQUIRE(!a->ln_out16 || (a->ld_ln_out16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a->ln_out16) & 15) == 0),
+                "iir_gemm_tc: ln_out16 / ld_ln_out16 must be 16-byte aligned");
+    p.ln_stats_out = reinterpret_cast<long long*>(a->ln_stats_out); p.ln_out16 = a->ln_out16; p.ld_ln16 = a->ld_ln_out16;
+  } else {
+    IIR_REQUIRE(!a->ln_out16, "iir_gemm_tc: ln_out16 needs ln_stats_out");
+  }
+  if (a->ln_stats_in) {
+    IIR_REQUIRE(a->ln_colsum && a->bias && !a->conv && a->pair != IIR_PAIR_SFT,
+                "iir_gemm_tc: ln_stats_in needs ln_colsum, bias (= W beta + b) and a linear problem");
+    IIR_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->ln_stats_zero) & 15) == 0,
+                "iir_gemm_tc: ln_stats_in / ln_stats_zero must be 16-byte aligned");
+    p.ln_stats_in = reinterpret_cast<const long long*>(a->ln_stats_in);
+    p.ln_stats_zero = reinterpret_cast<long long*>(a->ln_stats_zero);
+    p.ln_colsum = a->ln_colsum;
+    p.ln_inv_k = 1.0f / static_cast<float>(a->K); p.ln_eps = a->ln_eps;
+  } else {
+    IIR_REQUIRE(!a->ln_stats_zero, "iir_gemm_tc: ln_stats_zero needs ln_stats_in");
+  }
 
   const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;
   // staging slots per epilogue warp: enough for this warp's chunks of the tile when an fp32 residual is
@@ -579,15 +664,15 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     if (slots > 3) slots = 3;
     int want = mma2 ? 6 : 4;
     if (want > p.num_kb + 1) want = p.num_kb + 1;
-    while (slots > 1 && (227 * 1024 - 1024 - 256 - 2048 - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
+    while (slots > 1 && (227 * 1024 - 1024 - 256 - VEC_BYTES - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
   }
   p.epi_slots = slots;
   const int epi_bytes = 8 * slots * EPI_STAGE_BYTES;
-  int stages = (227 * 1024 - 1024 - 256 - 2048 - epi_bytes) / stage_bytes;
+  int stages = (227 * 1024 - 1024 - 256 - VEC_BYTES - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 2048 + epi_bytes;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + VEC_BYTES + epi_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
 
   const int num_tiles = p.tiles_m_cl * p.tiles_n;  // super-tiles, one per cluster at a time

@@ -103,17 +103,55 @@ def _conv_to_gemm(w):  # [Co,Ci,k,k] -> [Co, k*k*Ci] tap-major
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
-def _load_w(rt, src, name, transform=None, lora_ok=True):
-    """returns _Packed of the (transformed) weight in rt.w_dtype; merges LoRA when the source has it."""
+def _load_w(rt, src, name, transform=None, lora_ok=True, fold=None, bias=None):
+    """returns _Packed of the (transformed) weight in rt.w_dtype; merges LoRA when the source has it.
+
+    fold = (gamma, beta) of the LayerNorm in front of this linear (folded-LN GEMM, include/instantir_b200.h):
+    the packed weight becomes W' = W∘gamma and the result carries ``.colsum`` = Σ_k W'[n,k] (of the ROUNDED
+    weight, so that the mean term cancels exactly what the tensor cores accumulate) and ``.bias`` = W·beta + b,
+    each with a LoRA-merged twin when the weight has one."""
     w = src.get(name + ".weight")
-    tw = transform(w) if transform else w
-    base = tw.to(rt.w_dtype).contiguous()
+
+    def pack(w_):
+        t = w_.float() * fold[0].float()[None, :] if fold is not None else w_
+        t = transform(t) if transform else t
+        return t.to(rt.w_dtype).contiguous()
+
+    def extras(w_, packed):
+        t = transform(w_.float()) if transform else w_.float()
+        b = t @ fold[1].float()
+        if bias is not None:
+            b = b + bias.float()
+        return packed.float().sum(1).contiguous(), b.contiguous()
+
+    base = pack(w)
     lw = None
     lo = src.get_lora(name) if lora_ok else None
+    m = None
     if lo is not None:
         m = merge_lora(w, lo)
-        lw = (transform(m) if transform else m).to(rt.w_dtype).contiguous()
-    return _Packed(rt, base, lw)
+        lw = pack(m)
+    out = _Packed(rt, base, lw)
+    if fold is not None:
+        cs, bf = extras(w, base)
+        cs_l = bf_l = None
+        if m is not None:
+            cs_l, bf_l = extras(m, lw)
+        out.colsum, out.bias = _Packed(rt, cs, cs_l), _Packed(rt, bf, bf_l)
+    return out
+
+
+class LNStream:
+    """The fp32 residual stream of a transformer stack plus what the folded-LayerNorm GEMMs exchange: a 16-bit
+    copy (the consumers' A operand) and per-row fixed-point (sum, sum of squares) accumulated by whichever GEMM
+    last updated the stream.  Quacks like the [B, n, C] hidden-states tensor the processors expect."""
+
+    def __init__(self, rt, h, B, n, C, eps):
+        self.rt, self.h, self.B, self.n, self.C, self.eps = rt, h, B, n, C, eps
+        self.h16 = rt.empty(B * n, C)
+        self.acc = torch.zeros(2, B * n, 2, device=rt.device, dtype=torch.int64)  # alternating row-sum accumulators
+        self.cur = 0
+        self.shape = (B, n, C)
 
 
 def _bias(src, name):
@@ -123,17 +161,25 @@ def _bias(src, name):
 class Linear:
     """nn.Linear on [M,K] activations (module/min_sdxl.py:301-307 etc.) with fused epilogues."""
 
-    def __init__(self, rt, src, name, bias=True):
+    def __init__(self, rt, src, name, bias=True, fold=None):
         self.rt = rt
-        self.w = _load_w(rt, src, name)
         self.b = _bias(src, name) if bias else None
+        self.w = _load_w(rt, src, name, fold=fold, bias=self.b)
+        self.folded = fold is not None
         self.N, self.K = self.w.base.shape
 
-    def __call__(self, a, M, out=None, out_dtype=None, residual=None, act=ops.ACT_NONE):
+    def __call__(self, a, M, out=None, out_dtype=None, residual=None, act=ops.ACT_NONE, ln_out=None):
         rt = self.rt
         if out is None:
             out = torch.empty(M, self.N, device=rt.device, dtype=out_dtype or rt.act_dtype)
-        ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.b, residual=residual, act=act, tc=rt.tc)
+        if isinstance(a, LNStream) != self.folded:
+            raise ops._lib.IIRError("a LayerNorm-folded linear takes the LNStream of its transformer block (and only it)")
+        if self.folded:
+            ops.gemm(a.h16, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.w.bias.get(), residual=residual, act=act,
+                     tc=True, ln_in=(a, self.w.colsum.get(), a.eps))
+        else:
+            ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.b, residual=residual, act=act, tc=rt.tc,
+                     ln_out=ln_out)
         return out
 
 

@@ -154,8 +154,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          residual=None, ld_res: Optional[int] = None, aux=None, ld_aux: Optional[int] = None,
          ld_out: Optional[int] = None, act: int = ACT_NONE, pair: int = PAIR_NONE,
          bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True,
-         cluster: Optional[int] = None):
-    """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1."""
+         cluster: Optional[int] = None, ln_out=None, ln_in=None):
+    """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1.
+
+    Folded LayerNorm (tc only, include/instantir_b200.h): ``ln_out`` = object with ``.acc`` ([2, M, 2] int64: two
+    alternating row-sum accumulators, zero-initialised), ``.cur`` (index of the live one) and ``.h16`` ([M, N]
+    16-bit): this GEMM adds the sums of its rows into ``acc[cur]`` and writes ``h16`` next to ``out``.  ``ln_in`` =
+    (such an object, colsum [N] fp32, eps): A must be its ``.h16``; clears ``acc[cur ^ 1]`` and flips ``cur``."""
     lib = _L(a, w, out)
     n_out = N // 2 if pair else N
     g = _lib.GemmArgs()
@@ -189,6 +194,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if cluster is None:
         cluster = tuned["cluster"] if tuned else 0
     g.bn, g.cluster = bn, cluster
+    if ln_out is not None:
+        g.ln_stats_out, g.ln_out16, g.ld_ln_out16 = _p(ln_out.acc[ln_out.cur]), _p(ln_out.h16), ln_out.h16.stride(0)
+    if ln_in is not None:
+        st, colsum, eps = ln_in
+        g.ln_stats_in, g.ln_stats_zero = _p(st.acc[st.cur]), _p(st.acc[st.cur ^ 1])
+        g.ln_colsum, g.ln_eps = _p(_f32c(colsum, "ln colsum")), eps
+        st.cur ^= 1  # the next producer adds into the accumulator this launch clears
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
     with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=key, epi=epi,

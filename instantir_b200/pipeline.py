@@ -27,6 +27,7 @@ from typing import List, Optional
 import torch
 
 from . import _lib, ops
+from .nn import FMap
 from .schedulers import _randn
 
 
@@ -140,7 +141,7 @@ class InstantIRPipeline:
                  init_latents_with_lq=True, multistep_restore=False, adastep_restore=False, previewer_scheduler=None,
                  preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                  controlnet_conditioning_scale=1.0, reference_latents=None, use_cuda_graph=True, cfg_parallel=None,
-                 dp_shard=None, record=None, overlap_streams=True, **kwargs):
+                 dp_shard=None, record=None, overlap_streams=True, agg_ahead=False, **kwargs):
         if prompt is not None or negative_prompt is not None or ip_adapter_image is not None:
             raise NotImplementedError("text / image encoders are outside this build's scope (SURVEY §8 f1-f2): pass "
                                       "prompt_embeds, pooled_prompt_embeds, ip_adapter_image_embeds and a latent `image`")
@@ -264,12 +265,69 @@ class InstantIRPipeline:
                     return eps, down, mid
                 return run
 
+            # ---- aggregator one step AHEAD.  On a step that does not preview, the Aggregator's inputs are the LQ
+            # latent (as sample AND as controlnet_cond, pipelines/sdxl_instantir.py:1578-1593), the prompt and the
+            # timestep: nothing that depends on the current latents.  So the Aggregator of step i+1 runs on the side
+            # stream beside the WHOLE UNet of step i (not only beside its down path), into the other of two residual
+            # sets; the first such step of a run pays one stand-alone Aggregator.  Opt-in (`agg_ahead=True`): measured
+            # on B200 it is NOT faster than the in-order fork (37.4 vs 36.0 ms/step) — two tcgen05 GEMM CTAs cannot
+            # share an SM (each takes all 512 TMEM columns and > 113 KB of shared memory), so kernels of the two
+            # streams mostly take turns whatever the schedule.
+            S.t_next = torch.empty(1, **f32)
+            S.res_buf = None
+
+            def res_buffers():
+                if S.res_buf is None:  # shapes from one eager forward (also the kernels' lazy-init warm-up)
+                    down, mid = agg(image_all, t_dev, encoder_hidden_states=prompt_all, controlnet_cond=image_all,
+                                    added_cond_kwargs=agg_added, return_dict=False)
+
+                    def like(r):
+                        nn_, C_, H_, W_ = r.shape
+                        return torch.empty(nn_ * H_ * W_, C_, device=r.device, dtype=r.dtype)
+
+                    S.res_buf = [([like(r) for r in down], like(mid)) for _ in range(2)]
+                    S.res_view = [([FMap(b, r.shape[0], r.shape[2], r.shape[3], r.shape[1]).nchw() for b, r in zip(bd, down)],
+                                   FMap(bm, mid.shape[0], mid.shape[2], mid.shape[3], mid.shape[1]).nchw()) for bd, bm in S.res_buf]
+                return S.res_buf
+
+            def f_agg_into(p):
+                def run():
+                    agg(image_all, t_dev, encoder_hidden_states=prompt_all, controlnet_cond=image_all,
+                        added_cond_kwargs=agg_added, return_dict=False, out_buffers=res_buffers()[p])
+                return run
+
+            def f_unet_buf(p):
+                def run():
+                    res_buffers()
+                    return unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added,
+                                down_block_additional_residuals=S.res_view[p][0], mid_block_additional_residual=S.res_view[p][1],
+                                additional_residual_scale=cond_scale, return_dict=False)[0]
+                return run
+
+            def f_pipe(p):
+                def run():
+                    bufs = res_buffers()
+                    cur = torch.cuda.current_stream()
+                    S.side.wait_stream(cur)
+                    with torch.cuda.stream(S.side):
+                        agg(image_all, S.t_next, encoder_hidden_states=prompt_all, controlnet_cond=image_all,
+                            added_cond_kwargs=agg_added, return_dict=False, out_buffers=bufs[1 - p])
+                    eps = unet(x_in, t_dev, encoder_hidden_states=prompt_all, added_cond_kwargs=added,
+                               down_block_additional_residuals=S.res_view[p][0], mid_block_additional_residual=S.res_view[p][1],
+                               additional_residual_scale=cond_scale, return_dict=False)[0]
+                    cur.wait_stream(S.side)
+                    return eps
+                return run
+
+            S.g_agg_into = [_Graphed(f_agg_into(p), use_cuda_graph) for p in range(2)]
+            S.g_pipe = [_Graphed(f_pipe(p), use_cuda_graph) for p in range(2)]
             S.g_step = {"prev": _Graphed(f_step(preview_latent), use_cuda_graph), "lq": _Graphed(f_step(image_all), use_cuda_graph)}
             S.g_preview = _Graphed(f_preview, use_cuda_graph)
             S.g_agg_prev = _Graphed(f_agg(preview_latent), use_cuda_graph)
             S.g_agg_lq = _Graphed(f_agg(image_all), use_cuda_graph)
             # one graph per residual source: the captured UNet reads the static outputs of that aggregator graph
-            S.g_unet_res = {"prev": _Graphed(f_unet(True), use_cuda_graph), "lq": _Graphed(f_unet(True), use_cuda_graph)}
+            S.g_unet_res = {"prev": _Graphed(f_unet(True), use_cuda_graph), "lq": _Graphed(f_unet(True), use_cuda_graph),
+                            "buf0": _Graphed(f_unet_buf(0), use_cuda_graph), "buf1": _Graphed(f_unet_buf(1), use_cuda_graph)}
             S.g_unet_plain = _Graphed(f_unet(False), use_cuda_graph)
         else:
             for k, v in new.items():
@@ -279,7 +337,12 @@ class InstantIRPipeline:
         g_preview, g_agg_prev, g_agg_lq, g_unet_res, g_unet_plain = S.g_preview, S.g_agg_prev, S.g_agg_lq, S.g_unet_res, S.g_unet_plain
         g_step = S.g_step if overlap_streams else None
         unet.refresh_context(S.prompt_all, S.added, None)
-        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts)
+        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts, ahead=None)
+        ahead_ok = g_step is not None and agg_ahead
+
+        def lq_step(j):
+            """step j runs the Aggregator on the LQ latent alone (no preview): its output depends only on t_j"""
+            return j < n and min(1.0, float(scales[j])) * keep[j] > 0.1 and not previewing[j] > 0
 
         def step(i):
             """one denoising step of the schedule (pipelines/sdxl_instantir.py:1497-1666)."""
@@ -302,7 +365,25 @@ class InstantIRPipeline:
                     loop.res_src = "prev"
                 else:
                     loop.res_src = "lq"
-                if g_step is not None:
+                if not previewed and ahead_ok:
+                    # Aggregator(t_i) was computed beside the UNet of step i-1 (or is computed now, once per run);
+                    # Aggregator(t_{i+1}) runs beside this step's UNet
+                    if loop.ahead is not None and loop.ahead[0] == i:
+                        p = loop.ahead[1]
+                    else:
+                        p = 0
+                        S.g_agg_into[p]()
+                    if lq_step(i + 1):
+                        S.t_next.fill_(float(int(ts[i + 1])))
+                        noise_pred = S.g_pipe[p]()
+                        loop.ahead = (i + 1, 1 - p)
+                    else:
+                        noise_pred = g_unet_res[f"buf{p}"]()
+                        loop.ahead = None
+                    st.down, st.mid = S.res_view[p]
+                    loop.res_src = f"buf{p}"
+                elif g_step is not None:
+                    loop.ahead = None
                     noise_pred, st.down, st.mid = g_step[loop.res_src]()   # aggregator || UNet down+mid, then UNet up
                 else:
                     st.down, st.mid = (g_agg_prev if previewed else g_agg_lq)()

@@ -12,6 +12,7 @@ the concat kernel of the up path.
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import List, Optional
 
@@ -20,7 +21,7 @@ import torch
 from . import ops
 from .attention_processor import Attention, AttnProcessor2_0, CtxCache, silu_of
 from .config import ModelConfig
-from .nn import (Conv3x3, Downsample2D, FMap, GroupNorm, LayerNorm, Linear, ResnetBlock2D, Runtime, SmallLinear,
+from .nn import (Conv3x3, Downsample2D, FMap, GroupNorm, LayerNorm, Linear, LNStream, ResnetBlock2D, Runtime, SmallLinear,
                  Upsample2D, _bias, _load_w, _pack_pairs, _Packed, fmap_from_nchw)
 from .resampler import MultiIPAdapterImageProjection, Resampler
 
@@ -29,7 +30,7 @@ class GEGLUFeedForward:
     """FeedForward(GEGLU) (module/min_sdxl.py:502-528): proj GEMM with the x1*gelu(x2) product fused
     into its epilogue (weights pair-packed per N tile), then the output GEMM with bias+residual."""
 
-    def __init__(self, rt, src, p, C):
+    def __init__(self, rt, src, p, C, fold=None):
         self.rt, self.C = rt, C
         self.bn = ops.default_bn(8 * C, pair=True)
         bn = self.bn
@@ -37,13 +38,22 @@ class GEGLUFeedForward:
         def pack(w):
             return _pack_pairs(w[: 4 * C], w[4 * C:], bn)
 
-        self.w1 = _load_w(rt, src, p + ".net.0.proj", pack)
         self.b1 = pack(src.get(p + ".net.0.proj.bias")).contiguous()
+        self.w1 = _load_w(rt, src, p + ".net.0.proj", pack, fold=fold, bias=self.b1)
+        self.folded = fold is not None
         self.out = Linear(rt, src, p + ".net.2")
 
     def __call__(self, a, M, residual, out_dtype=None):
+        """a: normalised activations, or the block's LNStream when norm3 is folded (then `residual` is it too)."""
         rt, C = self.rt, self.C
         g = rt.empty(M, 4 * C)
+        if self.folded:
+            st = a
+            ops.gemm(st.h16, self.w1.get(), g, M=M, N=8 * C, K=C, bias=self.w1.bias.get(), pair=ops.PAIR_GEGLU, bn=self.bn,
+                     tc=True, ln_in=(st, self.w1.colsum.get(), st.eps))
+            if out_dtype is None:  # in place on the fp32 stream, refreshing its 16-bit copy + row statistics
+                return self.out(g, M, out=st.h, residual=st.h, ln_out=st)
+            return self.out(g, M, out_dtype=out_dtype, residual=st.h)
         ops.gemm(a, self.w1.get(), g, M=M, N=8 * C, K=C, bias=self.b1, pair=ops.PAIR_GEGLU, bn=self.bn, tc=rt.tc)
         if out_dtype is None:  # in-place on the fp32 stream
             return self.out(g, M, out=residual, residual=residual)
@@ -55,18 +65,31 @@ class BasicTransformerBlock:
 
     def __init__(self, rt, src, p, C, heads, cross_dim):
         self.rt, self.C = rt, C
+        # tcgen05 path: the three LayerNorms are folded into the GEMMs on either side of them (nn.LNStream,
+        # DESIGN.md §3.2); the fp32 check mode runs them as kernels
+        self.fold_ln = rt.tc and os.environ.get("IIR_LN_FOLD", "1") != "0"
         self.norm1 = LayerNorm(rt, src, p + ".norm1", C)
-        self.attn1 = Attention(rt, src, p + ".attn1", C, heads)
+        self.attn1 = Attention(rt, src, p + ".attn1", C, heads, fold=self._fold(self.norm1))
         self.attn2 = None
         if cross_dim is not None:
             self.norm2 = LayerNorm(rt, src, p + ".norm2", C)
-            self.attn2 = Attention(rt, src, p + ".attn2", C, heads, cross_dim)
+            self.attn2 = Attention(rt, src, p + ".attn2", C, heads, cross_dim, fold=self._fold(self.norm2))
         self.norm3 = LayerNorm(rt, src, p + ".norm3", C)
-        self.ff = GEGLUFeedForward(rt, src, p + ".ff", C)
+        self.ff = GEGLUFeedForward(rt, src, p + ".ff", C, fold=self._fold(self.norm3))
+
+    def _fold(self, norm):
+        return (norm.g, norm.b) if self.fold_ln else None
 
     def __call__(self, h, B, n, encoder_hidden_states, kw, last):
-        """h: fp32 stream [B*n, C], updated in place; returns act-dtype tensor when `last`."""
+        """h: fp32 stream [B*n, C] (or its LNStream on the folded path), updated in place; returns an act-dtype
+        tensor when `last`."""
         M, C = B * n, self.C
+        if self.fold_ln:
+            st = h
+            self.attn1(st, encoder_hidden_states=None, residual=st, **kw)
+            if self.attn2 is not None:
+                self.attn2(st, encoder_hidden_states=encoder_hidden_states, residual=st, **kw)
+            return self.ff(st, M, residual=st, out_dtype=self.rt.act_dtype if last else None)
         h3 = h.view(B, n, C)
         self.attn1(self.norm1(h, M).view(B, n, C), encoder_hidden_states=None, residual=h3, **kw)
         if self.attn2 is not None:
@@ -89,7 +112,11 @@ class Transformer2DModel:
     def __call__(self, x: FMap, encoder_hidden_states, kw) -> FMap:
         n_tok = x.H * x.W
         a = self.norm(x, silu=False)
-        h = self.proj_in(a.t, x.M, out_dtype=torch.float32)
+        if self.transformer_blocks[0].fold_ln:
+            h = LNStream(self.rt, self.rt.stream(x.M, self.C), x.n, n_tok, self.C, self.transformer_blocks[0].norm1.eps)
+            self.proj_in(a.t, x.M, out=h.h, ln_out=h)
+        else:
+            h = self.proj_in(a.t, x.M, out_dtype=torch.float32)
         y = h
         for k, blk in enumerate(self.transformer_blocks):
             y = blk(h, x.n, n_tok, encoder_hidden_states, kw, last=k == len(self.transformer_blocks) - 1)

@@ -119,6 +119,70 @@ def _conv_ref(x_nhwc, w_packed, bias, stride=1, up2=False):
     return y.permute(0, 2, 3, 1).reshape(-1, co)
 
 
+# ------------------------------------------------------------------ LayerNorm folded into GEMMs
+class _Stream:
+    def __init__(self, M, C):
+        self.h16 = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        self.acc = torch.zeros(2, M, 2, device=DEV, dtype=torch.int64)
+        self.acc[1] = 12345  # the consumer must clear it for the next producer
+        self.cur = 0
+
+
+@pytest.mark.parametrize("M,C,N2,bn_prod,bn_cons,residual,cluster", [
+    (2048, 1280, 3840, None, None, True, None), (300, 320, 320, 96, 64, True, 1), (1024, 640, 1920, 256, 160, False, 2),
+    (515, 1280, 1280, 192, 224, True, None), (256, 64, 64, 32, 32, True, 1)])
+def test_gemm_folded_layernorm(M, C, N2, bn_prod, bn_cons, residual, cluster):
+    """producer GEMM writes the fp32 stream + its 16-bit copy + per-row partial sums; consumer GEMM on that copy
+    with W' = W*gamma, colsum, b' equals Linear(LayerNorm(stream)) (include/instantir_b200.h, folded LN)."""
+    K0, eps = 256, 1e-5
+    a = rnd(M, K0, seed=1, dtype=torch.bfloat16)
+    w0 = rnd(C, K0, seed=2, scale=K0 ** -0.5, dtype=torch.bfloat16)
+    b0 = rnd(C, seed=3)
+    res = rnd(M, C, seed=4, scale=2.0) + 0.5 if residual else None
+    st = _Stream(M, C)
+    h = res.clone() if residual else torch.empty(M, C, device=DEV)
+    ops.gemm(a, w0, h, M=M, N=C, K=K0, bias=b0, residual=h if residual else None, bn=bn_prod, cluster=cluster, ln_out=st)
+    torch.cuda.synchronize()
+    h_ref = a.float() @ w0.float().t() + b0 + (res if residual else 0)
+    assert rel_l2(h, h_ref) < 3e-3
+    assert torch.equal(st.h16, h.to(torch.bfloat16))
+    assert torch.allclose(st.acc[0, :, 0].double() / 2.0 ** 32, h.double().sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st.acc[0, :, 1].double() / 2.0 ** 24, (h.double() ** 2).sum(1), rtol=1e-5, atol=1e-3)
+    gamma, beta = 1.0 + 0.3 * rnd(C, seed=5), 0.2 * rnd(C, seed=6)
+    w = rnd(N2, C, seed=7, scale=C ** -0.5)
+    b = rnd(N2, seed=8)
+    wf = (w * gamma[None, :]).to(torch.bfloat16)
+    colsum = wf.float().sum(1).contiguous()
+    bf = (w @ beta + b).contiguous()
+    out = torch.full((M, N2), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(st.h16, wf, out, M=M, N=N2, K=C, bias=bf, bn=bn_cons, cluster=cluster, ln_in=(st, colsum, eps))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(h, (C,), gamma, beta, eps) @ w.t() + b
+    assert rel_l2(out, ref) < 8e-3
+    assert st.cur == 1 and int(st.acc[1].abs().max()) == 0
+
+
+def test_gemm_folded_layernorm_geglu_consumer():
+    M, C, eps, bn = 640, 320, 1e-5, 256
+    h = rnd(M, C, seed=1, scale=1.5) + 0.3
+    st = _Stream(M, C)
+    # producer: identity-free path, write stats through a 1-tile GEMM with zero weights + residual
+    z = torch.zeros(M, 64, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(z, torch.zeros(C, 64, device=DEV, dtype=torch.bfloat16), h, M=M, N=C, K=64, residual=h, ln_out=st)
+    gamma, beta = 1.0 + 0.3 * rnd(C, seed=5), 0.2 * rnd(C, seed=6)
+    w = rnd(8 * C, C, seed=7, scale=C ** -0.5)
+    b = rnd(8 * C, seed=8)
+    wp, bp = pack_pairs(w * gamma[None, :], w @ beta + b, bn)
+    wp16 = wp.to(torch.bfloat16)
+    out = torch.empty(M, 4 * C, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(st.h16, wp16, out, M=M, N=8 * C, K=C, bias=bp.contiguous(), pair=ops.PAIR_GEGLU, bn=bn,
+             ln_in=(st, wp16.float().sum(1).contiguous(), eps))
+    torch.cuda.synchronize()
+    y = F.layer_norm(h, (C,), gamma, beta, eps) @ w.t() + b
+    ref = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+    assert rel_l2(out, ref) < 8e-3
+
+
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("n,H,W,Cin,Cout,bn", [(2, 16, 16, 64, 128, 128), (1, 32, 32, 128, 64, 64), (2, 32, 32, 64, 320, None),
                                                (4, 8, 8, 64, 64, 64), (2, 64, 32, 64, 192, 64),

@@ -89,7 +89,7 @@ def test_resampler_vs_reference_vector(precision):
 
 
 def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0, cge=1.0, graph=True, guidance=7.0,
-              timesteps=None):
+              timesteps=None, **pipe_kw):
     oc = getattr(ocfg, cfg_name)()
     alpha = 8.0
     ounet, oagg = build_oracle(oc, seed=0, lora_alpha=alpha)
@@ -115,7 +115,7 @@ def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0,
                ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=None if timesteps else steps, timesteps=timesteps,
                guidance_scale=guidance,
                previewer_scheduler=LCMSingleStepScheduler(), preview_start=preview_start, control_guidance_end=cge,
-               generator=torch.Generator().manual_seed(42), use_cuda_graph=graph, record=rec_p)
+               generator=torch.Generator().manual_seed(42), use_cuda_graph=graph, record=rec_p, **pipe_kw)
     torch.cuda.synchronize()
     return ref, rec_o, out.images, rec_p
 
@@ -217,6 +217,44 @@ def test_step_shapes_no_preview_and_unet_only_fp32():
     ref, rec_o, out, rec_p = _run_pair("fp32", preview_start=1.0, cge=0.5, graph=True)
     for a, b in zip(rec_p["latents"], rec_o["latents"]):
         assert rel_l2(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_aggregator_one_step_ahead_fp32(graph):
+    """No previewer: the Aggregator of step i+1 runs beside the UNet of step i (pipeline.py, `agg_ahead`).  Four
+    steps cover the stand-alone first Aggregator, both residual sets, and the last step (nothing to run ahead);
+    with control_guidance_end = 0.75 the fourth step is UNet-only.  Against the oracle, and bit-identical to the
+    in-order schedule (same kernels on the same inputs, only enqueued earlier)."""
+    for cge in (1.0, 0.75):
+        ref, rec_o, out, rec_p = _run_pair("fp32", steps=4, preview_start=1.0, cge=cge, graph=graph, agg_ahead=True)
+        for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+            assert rel_l2(a, b) < 1e-4, f"cge {cge} step {i}"
+        _, _, out_inorder, _ = _run_pair("fp32", steps=4, preview_start=1.0, cge=cge, graph=graph, agg_ahead=False)
+        assert torch.equal(out, out_inorder)
+
+
+def test_aggregator_ahead_mixed_with_preview_steps_bf16():
+    """preview_end = 0.5: steps 0-1 preview (Aggregator fed the preview latent, in order), steps 2-3 do not (run
+    ahead).  bf16 tcgen05 path with the folded LayerNorm; bit-identical to the in-order schedule."""
+    oc = ocfg.tiny()
+    alpha = 8.0
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=alpha)
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = _pcfg_from(oc)
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=alpha / oc.lora_rank), DEV, "bf16")
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, "bf16")
+    outs = []
+    for ahead in (True, False):
+        pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+        outs.append(pipe(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                         pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+                         ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=4, guidance_scale=7.0,
+                         previewer_scheduler=LCMSingleStepScheduler(), preview_start=0.0, preview_end=0.5,
+                         generator=torch.Generator().manual_seed(42), agg_ahead=ahead).images.clone())
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
 def test_guidance_scale_le_1_disables_cfg_fp32():

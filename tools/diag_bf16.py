@@ -12,6 +12,11 @@ torch.set_grad_enabled(False)
 DEV = "cuda"
 oc = ocfg.tiny(); alpha = 8.0
 ounet, oagg = build_oracle(oc, 0, alpha)
+if os.environ.get("IIR_DIAG_ROUND_W") == "1":  # weights as a 16-bit checkpoint would hold them: exactly bf16-representable
+    for m in (ounet, oagg):
+        for p_ in m.parameters():
+            p_.data = p_.data.to(torch.bfloat16).float()
+    print("oracle weights rounded to bf16-representable values")
 inp = make_inputs(oc)
 usd, ulora = export_state(ounet); asd, _ = export_state(oagg)
 pc = pcfg.ModelConfig(**oc.to_dict())

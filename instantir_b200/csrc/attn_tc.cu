@@ -342,12 +342,17 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
   uint64_t* s_empty = s_full + 1;                      // 1
   uint64_t* p_full = s_empty + 1;                      // 2: P columns [0,32) / [32,64) written
   uint64_t* p_empty = p_full + 2;                      // 2: the MMAs reading that half of P retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+  uint64_t* q_empty = p_empty + 2;                     // 1: the Q K^T MMAs of a tile retired, sQ may be refilled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   pdl_trigger();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  // persistent: CTA c walks tiles c, c + grid, ... (tile = (batch, head, 128-query block), query block fastest so
+  // that co-running CTAs share one head's K/V in L2); barriers, TMEM and the K/V ring live across tiles, and the
+  // producer runs ahead into the next tile while the softmax of the current one finishes
+  const int nqt = (p.n_q + 127) >> 7;
+  const int total_tiles = nqt * p.heads * p.B;
   const int nb = PERBLOCK ? p.n_seg : p.nblk[0];
 
   if (warp == 4 && lane == 0) {
@@ -359,6 +364,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       tma_prefetch_desc(&p.tmV[1]);
     }
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(s_empty, 128);
     for (int hh = 0; hh < 2; ++hh) {
@@ -387,66 +393,79 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
     // descriptors / coordinates in uniform registers) and elect one lane per instruction group.
     if (warp == 4) {
       // ---------------------------------------------------------------- TMA producer
-      if (elect_one()) {
-        mbar_expect_tx(q_full, TILE_BYTES);
-        tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
-      }
-      __syncwarp();
       int st = 0;
       uint32_t ph = 0;
-      for (int jb = 0; jb < nb; ++jb) {
-        mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int qt = tile % nqt, hb = tile / nqt;
+        const int h = hb % p.heads, b = hb / p.heads, q0 = qt * 128;
+        if (it > 0) mbar_wait_sleep(q_empty, (it - 1) & 1, 20000);  // Q K^T of the previous tile has read sQ
         if (elect_one()) {
-          mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-          const int sg = PERBLOCK ? jb : 0, jr = PERBLOCK ? 0 : jb * 128;
-          tma_load_3d(sK + st * TILE_BYTES, &p.tmK[sg], &kv_full[st], p.k_off[sg] + h * 64, jr, b);
-          tma_load_3d(sV + st * TILE_BYTES, &p.tmV[sg], &kv_full[st], p.v_off[sg] + h * 64, jr, b);
+          mbar_expect_tx(q_full, TILE_BYTES);
+          tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
         }
         __syncwarp();
-        if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
+        for (int jb = 0; jb < nb; ++jb) {
+          mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
+          if (elect_one()) {
+            mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+            const int sg = PERBLOCK ? jb : 0, jr = PERBLOCK ? 0 : jb * 128;
+            tma_load_3d(sK + st * TILE_BYTES, &p.tmK[sg], &kv_full[st], p.k_off[sg] + h * 64, jr, b);
+            tma_load_3d(sV + st * TILE_BYTES, &p.tmV[sg], &kv_full[st], p.v_off[sg] + h * 64, jr, b);
+          }
+          __syncwarp();
+          if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
+        }
       }
     } else if (warp == 5) {
       // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // A (=P) K-major in TMEM, B (=V) MN-major
       // O += P_j V_j in two halves of 64 keys: the first half's MMAs run under the exps of the second
-      auto issue_pv = [&](int j, int st) {
+      // g = block counter over all tiles of this CTA (barrier parities), jl = block index inside the tile
+      auto issue_pv = [&](uint32_t g, int jl, int st) {
         const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV + st * TILE_BYTES), 1024, 1024);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          mbar_wait_sleep(&p_full[hh], j & 1, 2000);
+          mbar_wait_sleep(&p_full[hh], g & 1, 2000);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
             for (int k = hh * 4; k < hh * 4 + 4; ++k)  // +16 keys = +2048 B = +128 in the (addr >> 4) field
-              umma_ts_bf16(tmem_O, tmem_P + k * 8, vdesc0 + 128 * k, idesc_pv, (k != 0 || j != 0) ? 1u : 0u);
+              umma_ts_bf16(tmem_O, tmem_P + k * 8, vdesc0 + 128 * k, idesc_pv, (k != 0 || jl != 0) ? 1u : 0u);
             if (hh == 1) umma_commit(&kv_empty[st]);
             umma_commit(&p_empty[hh]);  // this half of P is free; after hh == 1, O is stable
           }
           __syncwarp();
         }
       };
-      mbar_wait(q_full, 0);
       const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
       int st = 0, st_prev = 0;
-      uint32_t ph = 0;
-      for (int jb = 0; jb < nb; ++jb) {
-        mbar_wait_sleep(&kv_full[st], ph, 2000);
-        mbar_wait_sleep(s_empty, (jb & 1) ^ 1, 2000);
-        tc_fence_after();
-        const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
-        if (elect_one()) {
+      uint32_t ph = 0, g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        mbar_wait_sleep(q_full, it & 1, 2000);
+        for (int jb = 0; jb < nb; ++jb, ++g) {
+          mbar_wait_sleep(&kv_full[st], ph, 2000);
+          mbar_wait_sleep(s_empty, (g & 1) ^ 1, 2000);
+          tc_fence_after();
+          const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_S, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(s_full);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_S, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(s_full);
+            if (jb == nb - 1) umma_commit(q_empty);  // last read of this tile's Q
+          }
+          __syncwarp();
+          // P V of the previous block; the first P V of a tile overwrites O (accumulate = 0): the softmax warps
+          // signal its P only after their epilogue has read the previous tile's O out of TMEM
+          if (jb > 0) issue_pv(g - 1, jb - 1, st_prev);
+          st_prev = st;
+          if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (jb > 0) issue_pv(jb - 1, st_prev);
-        st_prev = st;
-        if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
+        issue_pv(g - 1, nb - 1, st_prev);
       }
-      issue_pv(nb - 1, st_prev);
     }
   } else {
     // ---------------------------------------------------------------- softmax warpgroup
@@ -457,13 +476,18 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
     const uint32_t trow = static_cast<uint32_t>(lane_base) << 16;
     const float sl2 = p.scale_log2;
     const float kLazy = 8.0f / sl2;  // advance the reference max only when exp2 arguments would exceed 8
+    uint32_t gb = 0;  // block counter over all tiles of this CTA: every per-block barrier completes once per block
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int qt = tile % nqt, hb = tile / nqt;
+    const int h = hb % p.heads, b = hb / p.heads, q0 = qt * 128;
     const int qi = q0 + row;
     bf16* optr = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
     float m_ref = -INFINITY, l_run = 0.f;
 #pragma unroll 1
-    for (int jb = 0; jb < nb; ++jb) {
+    for (int jb = 0; jb < nb; ++jb, ++gb) {
       const int valid = PERBLOCK ? min(128, p.kv_len[jb]) : min(128, p.kv_len[0] - jb * 128);
-      mbar_wait_sleep(s_full, jb & 1, 20000);
+      mbar_wait_sleep(s_full, gb & 1, 20000);
       tc_fence_after();
       uint32_t sr[128];
       {
@@ -514,7 +538,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
           for (int j = 0; j < 32; j += 2)
             pk[j >> 1] = pack_bf16(__uint_as_float(sr[g * 32 + j]) * wseg, __uint_as_float(sr[g * 32 + j + 1]) * wseg);
           if (g == 0 || g == 2) {
-            mbar_wait(&p_empty[g >> 1], (jb & 1) ^ 1);
+            mbar_wait(&p_empty[g >> 1], (gb & 1) ^ 1);
             tc_fence_after();
           }
           tmem_st16(tmem_P + trow + g * 16, pk);
@@ -555,7 +579,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       }
       if (__any_sync(0xffffffffu, grow)) {
         // rare: rescale O (TMEM) and l by exp2((m_old - mx) * sl2) for the rows that need it; O must be stable
-        mbar_wait(&p_empty[1], (jb & 1) ^ 1);
+        mbar_wait(&p_empty[1], (gb & 1) ^ 1);
         tc_fence_after();
         const float alpha = grow ? ex2_approx((m_old - mx) * sl2) : 1.0f;
         l_run *= alpha;
@@ -570,7 +594,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         }
         tmem_st_wait();
       }
-      mbar_wait(&p_empty[0], (jb & 1) ^ 1);  // first half of P V_{j-1} retired: P columns [0,32) are free
+      mbar_wait(&p_empty[0], (gb & 1) ^ 1);  // first half of P V_{j-1} retired: P columns [0,32) are free
       tc_fence_after();
       tmem_st16(tmem_P + trow, pk0);
       tmem_st16(tmem_P + trow + 16, pk1);
@@ -589,7 +613,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
           pk[j >> 1] = pack_bf16(e0, e1);
         }
         if (g == 2) {
-          mbar_wait(&p_empty[1], (jb & 1) ^ 1);  // all of P V_{j-1} retired
+          mbar_wait(&p_empty[1], (gb & 1) ^ 1);  // all of P V_{j-1} retired
           tc_fence_after();
         }
         tmem_st16(tmem_P + trow + g * 16, pk);
@@ -600,7 +624,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       mbar_arrive(&p_full[1]);
     }
     // all key blocks done: wait for the last P V, then O / l
-    mbar_wait(&p_empty[1], (nb - 1) & 1);
+    mbar_wait(&p_empty[1], (gb - 1) & 1);
     tc_fence_after();
     const float w = PERBLOCK ? 1.0f : p.seg_scale[0] / l_run;
 #pragma unroll 1
@@ -621,6 +645,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       }
     }
     tc_fence_before();
+    }  // tiles
   }
 
   tc_fence_before();
@@ -684,6 +709,9 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
 
   const size_t smem = 7 * TILE_BYTES + 256;
   dim3 grid((a->n_q + 127) / 128, a->heads, a->B);
+  // attn_ts kernels are persistent: two CTAs per SM walk the (batch, head, query block) tiles
+  const long long ats_tiles = static_cast<long long>(grid.x) * grid.y * grid.z;
+  const dim3 ats_grid(static_cast<unsigned>(ats_tiles < 2LL * sm_count() ? ats_tiles : 2LL * sm_count()));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   static int v1 = -1;
@@ -700,7 +728,7 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
 #define ATS_LAUNCH(PB, PL)                                                                                         \
   do {                                                                                                             \
     e = cudaFuncSetAttribute(attn_ts_kernel<PB, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<PB, PL>, grid, dim3(ATS_THREADS), smem, st, p);            \
+    if (e == cudaSuccess) e = launch_pdl(attn_ts_kernel<PB, PL>, ats_grid, dim3(ATS_THREADS), smem, st, p);            \
   } while (0)
   if (a->n_seg == 1 && !v1) {
     if (poly == 2) ATS_LAUNCH(false, 2);

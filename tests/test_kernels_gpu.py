@@ -281,6 +281,42 @@ def test_self_attention_fused_qkv(tc, B, heads, n):
     assert rel_l2(out, ref) < (8e-3 if tc else 2e-5)
 
 
+@pytest.mark.parametrize("B,heads,n", [(2, 20, 1024), (2, 10, 4096), (3, 20, 1000), (2, 20, 2048)])
+def test_self_attention_persistent_many_tiles(B, heads, n):
+    """more (batch, head, query-block) tiles than the 2 x 148 resident CTAs: every CTA of the persistent kernel
+    walks 2-3 tiles (barrier phases, K/V ring and TMEM carried across tiles); n = 1000 adds ragged last blocks.
+    Rows are compared per batch against fp32 SDPA; a second launch must give bit-identical results."""
+    C = heads * 64
+    qkv = rnd(B, n, 3 * C, seed=11, dtype=torch.bfloat16)
+    out = torch.full((B, n, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    args = (qkv, 0, 3 * C, [qkv], [C], [3 * C], [qkv], [2 * C], [3 * C], [n], [1.0])
+    ops.attention(*args, out, 0, C, B=B, heads=heads, n_q=n, softmax_scale=0.125)
+    out2 = torch.empty_like(out)
+    ops.attention(*args, out2, 0, C, B=B, heads=heads, n_q=n, softmax_scale=0.125)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.equal(out, out2)
+    for b in range(B):
+        ref = _sdpa_ref(qkv[b:b + 1, :, :C], qkv[b:b + 1, :, C:2 * C], qkv[b:b + 1, :, 2 * C:], heads, 0.125)
+        assert rel_l2(out[b:b + 1], ref) < 8e-3, b
+
+
+def test_cross_attention_persistent_many_tiles():
+    """the one-block-per-segment kernel (text 77 + image 64 keys) with 320 tiles on 296 resident CTAs"""
+    B, heads, n, nt, ni, scale_ip = 2, 20, 1024, 77, 64, 0.7
+    C = heads * 64
+    q = rnd(B, n, C, seed=1, dtype=torch.bfloat16)
+    kvt = rnd(B, nt, 2 * C, seed=2, dtype=torch.bfloat16)
+    ki = rnd(B, ni, C, seed=3, dtype=torch.bfloat16)
+    vi = rnd(B, ni, C, seed=4, dtype=torch.bfloat16)
+    out = torch.full((B, n, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, 0, C, [kvt, ki], [0, 0], [2 * C, C], [kvt, vi], [C, 0], [2 * C, C], [nt, ni],
+                  [1.0, scale_ip], out, 0, C, B=B, heads=heads, n_q=n, softmax_scale=0.125)
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(q, kvt[..., :C], kvt[..., C:], heads, 0.125) + scale_ip * _sdpa_ref(q, ki, vi, heads, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 8e-3
+
+
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("nt,ni", [(77, 64), (200, 64), (128, 1)])
 def test_decoupled_cross_attention_two_segments(tc, nt, ni):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 4
+#define IIR_ABI_VERSION 5
 
 typedef enum {
   IIR_OK = 0,
@@ -173,6 +173,12 @@ typedef struct {
 } iir_adaln_item;
 int iir_adaln_batched(const iir_adaln_item* items, int n_items, int rows, int rows_per_sample,
                       const float* mod, int64_t mod_ld, float eps, int out_dtype, void* stream);
+/* Row softmax: out[r, :] = softmax(x[r, :] * scale), x fp32 [rows, n] (leading dim ldx), out fp32 or 16-bit.
+ * The VAE decoder's mid-block attention has ONE head of dim 512 (diffusers UNetMidBlock2D as built by
+ * module/diffusers_vae/vae.py:239-249): S = Q K^T and O = P V run on the GEMM kernel, this normalises S.      */
+int iir_softmax_rows(const float* x, int64_t ldx, void* out, int out_dtype, int64_t ldo, int rows, int n,
+                     float scale, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * Data movement fused with the reference's elementwise steps

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
@@ -23,7 +23,7 @@ SYMBOLS = [
     "iir_abi_version", "iir_h16_dtype", "iir_last_error", "iir_launch_count",
     "iir_gemm_tc", "iir_gemm_simt", "iir_conv3x3_direct",
     "iir_attn_tc", "iir_attn_simt",
-    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched",
+    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add",
     "iir_timestep_embedding", "iir_linear_small",
     "iir_lcm_step", "iir_cfg_ddpm_step", "iir_add_noise",
@@ -94,6 +94,7 @@ def _declare(lib):
     lib.iir_groupnorm.argtypes = [vp, i, vp, vp, vp, i, i, i, i, i, f, i, vp, vp]
     lib.iir_layernorm.argtypes = [vp, i, vp, vp, vp, i64, i, vp, i, i, i, f, vp]
     lib.iir_adaln_batched.argtypes = [vp, i, i, i, vp, i64, f, i, vp]
+    lib.iir_softmax_rows.argtypes = [vp, i64, vp, i, i64, i, i, f, vp]
     lib.iir_concat_inject.argtypes = [vp, i, i, vp, i, vp, i, i, vp, i, vp, i, vp, i, i64, vp]
     lib.iir_upsample2x.argtypes = [vp, i, vp, i, i, i, i, i, vp]
     lib.iir_im2col3x3_s2.argtypes = [vp, i, vp, i, i, i, i, i, vp]

@@ -310,6 +310,56 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
 }
 
 
+// ---- row softmax: one CTA per row, three passes over the (L2-resident) row ---------------------------------
+// VAE mid-block attention (one head of dim 512): S = Q K^T is a GEMM, this normalises its rows.
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = is_max ? fmaxf(v, o) : v + o;
+  }
+  __syncthreads();  // red may still be read by the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, long long ldx, TO* __restrict__ out, long long ldo, int n,
+                    float scale_log2) {
+  __shared__ float red[8];
+  pdl_trigger();
+  pdl_wait();
+  const float* xr = x + blockIdx.x * ldx;
+  TO* orow = out + blockIdx.x * ldo;
+  const int nv = n >> 2;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = ld4(xr + i * 4);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = block_reduce(mx, red, true);
+  const float mneg = -mx * scale_log2;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = ld4(xr + i * 4);
+    sum += (exp2f(fmaf(v.x, scale_log2, mneg)) + exp2f(fmaf(v.y, scale_log2, mneg))) +
+           (exp2f(fmaf(v.z, scale_log2, mneg)) + exp2f(fmaf(v.w, scale_log2, mneg)));
+  }
+  sum = block_reduce(sum, red, false);
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    float4 v = ld4(xr + i * 4);
+    v.x = exp2f(fmaf(v.x, scale_log2, mneg)) * inv; v.y = exp2f(fmaf(v.y, scale_log2, mneg)) * inv;
+    v.z = exp2f(fmaf(v.z, scale_log2, mneg)) * inv; v.w = exp2f(fmaf(v.w, scale_log2, mneg)) * inv;
+    st4(orow + i * 4, v);
+  }
+}
+
 // ---- batched adaLN: one warp per row over n_items tensors of `rows` rows each ----------------
 template <typename TO>
 __global__ void __launch_bounds__(256)
@@ -496,4 +546,25 @@ extern "C" int iir_adaln_batched(const iir_adaln_item* items, int n_items, int r
   if (e != cudaSuccess) { set_error("iir_adaln_batched: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   return check_launch("iir_adaln_batched");
+}
+
+extern "C" int iir_softmax_rows(const float* x, int64_t ldx, void* out, int out_dtype, int64_t ldo, int rows, int n,
+                                float scale, void* stream) {
+  IIR_REQUIRE(x && out && rows > 0 && n > 0 && n % 4 == 0, "iir_softmax_rows: bad shape rows=%d n=%d (n%%4==0)", rows, n);
+  IIR_REQUIRE(ldx % 4 == 0 && ldo % (out_dtype == IIR_F32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "iir_softmax_rows: pointers / leading dims must be 16-byte aligned");
+  IIR_REQUIRE(dtype_ok(out_dtype), "iir_softmax_rows: unsupported dtype for this library build");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaError_t e;
+  if (out_dtype == IIR_F32)
+    e = launch_pdl(softmax_rows_kernel<float>, dim3(rows), dim3(256), 0, st, x, static_cast<long long>(ldx),
+                   reinterpret_cast<float*>(out), static_cast<long long>(ldo), n, sl2);
+  else
+    e = launch_pdl(softmax_rows_kernel<bf16>, dim3(rows), dim3(256), 0, st, x, static_cast<long long>(ldx),
+                   reinterpret_cast<bf16*>(out), static_cast<long long>(ldo), n, sl2);
+  if (e != cudaSuccess) { set_error("iir_softmax_rows: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
+  count_launch();
+  return check_launch("iir_softmax_rows");
 }

@@ -401,3 +401,15 @@ def add_noise(x0, noise, out, *, alpha_prod_t: float):
     _lib.check(lib.iir_add_noise(_p(_f32c(x0, "x0")), _p(_f32c(noise, "noise")), _p(_f32c(out, "out")),
                                  x0.numel(), alpha_prod_t, _stream()), "iir_add_noise", lib)
     return out
+
+
+def softmax_rows(x: torch.Tensor, out: torch.Tensor, *, scale: float):
+    """out[r, :] = softmax(x[r, :] * scale); x fp32 [rows, n] (row-contiguous), out fp32 or 16-bit."""
+    lib = _L(x, out)
+    if x.dtype != torch.float32 or x.ndim != 2 or out.ndim != 2 or x.stride(1) != 1 or out.stride(1) != 1 or x.shape != out.shape:
+        raise TypeError("softmax_rows: x fp32 [rows, n] and out [rows, n] with unit column stride")
+    rows, n = x.shape
+    with _Prof("softmax_rows", bytes=float(rows) * n * (3 * 4 + out.element_size())):
+        _lib.check(lib.iir_softmax_rows(_p(x), x.stride(0), _p(out), _dt(out), out.stride(0), rows, n, float(scale), _stream()),
+                   "iir_softmax_rows", lib)
+    return out

@@ -149,7 +149,10 @@ class InstantIRPipeline:
             raise NotImplementedError("multistep_restore / adastep_restore / guidance_rescale / denoising_end / "
                                       "reference_latents are experimental reference options (SURVEY §8 f4)")
         if output_type != "latent":
-            raise NotImplementedError("VAE decode is outside this build's scope (SURVEY §8 f1): use output_type='latent'")
+            if self.vae is None:
+                raise ValueError("output_type != 'latent' needs a VAE: InstantIRPipeline(unet, aggregator, scheduler, vae=AutoencoderKL(...))")
+            if output_type not in ("pt", "np"):
+                raise NotImplementedError(f"output_type={output_type!r}: 'latent', 'pt' and 'np' are built (SURVEY §8 f1)")
         self.check_inputs(image, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
                           negative_pooled_prompt_embeds, ip_adapter_image_embeds, guidance_scale,
                           control_guidance_start, control_guidance_end, previewer_scheduler, preview_start)
@@ -415,6 +418,13 @@ class InstantIRPipeline:
         for i in range(n):
             step(i)
         latents, preview_row = loop.latents, loop.preview_row
+        if output_type != "latent":
+            # pipelines/sdxl_instantir.py:1670-1704: latents / scaling_factor -> vae.decode -> postprocess.  The stock
+            # SDXL VAE config has no latents_mean / latents_std (:1676-1689); preview rows stay latents here.
+            from .vae import postprocess
+
+            image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False)[0]
+            latents = postprocess(image, output_type)
         if not return_dict:
             return (latents, preview_row) if save_preview_row else (latents,)
         return SimpleNamespace(images=latents, preview_rows=preview_row if save_preview_row else None)

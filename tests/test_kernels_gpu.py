@@ -542,3 +542,17 @@ def test_wrong_16bit_dtype_is_rejected_by_each_build():
         g.M = g.N = g.K = 64
         g.bn = 64
         assert lib.iir_gemm_tc(C.byref(g), None) == -1
+
+
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,n", [(5, 256), (300, 1024), (64, 16384), (3, 4104)])
+def test_softmax_rows(odt, rows, n):
+    x = rnd(rows, n, seed=3, scale=4.0)
+    x[0, 7] = 60.0  # a dominant logit
+    out = torch.full((rows, n), float("nan"), device=DEV, dtype=odt)
+    ops.softmax_rows(x, out, scale=0.37)
+    torch.cuda.synchronize()
+    ref = torch.softmax(x.double() * 0.37, dim=-1)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < (2e-6 if odt == torch.float32 else 4e-3)
+    assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=1e-5 if odt == torch.float32 else 2e-2)

@@ -154,3 +154,23 @@ def test_ddpm_schedule_and_closed_forms():
     # t=1 -> prev_t = -499 < 0 -> alpha_prev = 1: prev_sample == pred_original_sample
     assert rel(out.prev_sample, (x - (1 - a1) ** 0.5 * eps) / a1 ** 0.5) < 1e-6
     assert rel(out.prev_sample, out.pred_original_sample) < 1e-6
+
+
+def test_vae_decoder_vs_reference_run():
+    """oracle/vae.py Decoder vs the reference's vendored Decoder.forward run verbatim over the restated blocks, with
+    the reference's AttnProcessor2_0 in the mid block (tests/golden/make_golden_vae.py); SDXL VAE parameter count."""
+    from oracle import vae as ov
+
+    g = torch.load(os.path.join(G, "vae_decoder.pt"), weights_only=False)
+    cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    dec = ov.Decoder(cfg)
+    assert sorted(k for k, _ in dec.named_parameters()) == g["names"]
+    seeded_init(dec, g["seed"])
+    assert abs(checksum(dec) - g["checksum"]) < 1e-6 * g["checksum"]
+    with torch.no_grad():
+        out = dec(g["z"])
+    assert rel(out, g["out"]) < 1e-5
+    with torch.device("meta"):
+        full = ov.AutoencoderKLDecoder(ov.sdxl_vae())
+    # decoder half of the SDXL VAE (83.65 M parameters in total, 49,490,199 of them in post_quant_conv + decoder)
+    assert sum(p.numel() for p in full.parameters()) == 49_490_199

@@ -1,0 +1,123 @@
+"""SURVEY §8 row f1 (first "next" row): VAE decode on the sm_100a kernels against the oracle restatement and the
+reference-run Decoder vector; decoded-image PSNR of the whole config-1 path against the oracle (north star: >= 40 dB)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+from _util import build_oracle, export_state, make_inputs, rel_l2  # noqa: E402
+from seeding import seeded_init  # noqa: E402
+
+from instantir_b200 import config as pcfg  # noqa: E402
+from instantir_b200 import weights  # noqa: E402
+from instantir_b200.aggregator import Aggregator  # noqa: E402
+from instantir_b200.pipeline import InstantIRPipeline  # noqa: E402
+from instantir_b200.schedulers import DDPMScheduler, LCMSingleStepScheduler  # noqa: E402
+from instantir_b200.unet import UNet2DConditionModel  # noqa: E402
+from instantir_b200.vae import AutoencoderKL, VaeConfig, postprocess, vae_decoder_param_shapes  # noqa: E402
+from oracle import config as ocfg  # noqa: E402
+from oracle import pipeline as opipe  # noqa: E402
+from oracle import schedulers as osched  # noqa: E402
+from oracle import vae as ov  # noqa: E402
+
+torch.set_grad_enabled(False)
+DEV = "cuda"
+G = os.path.join(HERE, "golden")
+
+
+def _oracle_vae(cfg, seed=71):
+    vae = ov.AutoencoderKLDecoder(cfg)
+    seeded_init(vae, seed)
+    return vae.eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2), ("fp16", 4e-3)])
+def test_decoder_vs_reference_run_vector(precision, tol):
+    """product Decoder vs the vector produced by the reference's own Decoder.forward (tests/golden/make_golden_vae.py)"""
+    g = torch.load(os.path.join(G, "vae_decoder.pt"), weights_only=False)
+    cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    odec = ov.Decoder(cfg)
+    seeded_init(odec, g["seed"])
+    sd = {"decoder." + k: v for k, v in odec.state_dict().items()}
+    L = cfg.latent_channels
+    sd["post_quant_conv.weight"] = torch.eye(L).reshape(L, L, 1, 1)
+    sd["post_quant_conv.bias"] = torch.zeros(L)
+    vae = AutoencoderKL(VaeConfig(**cfg.to_dict()), weights.StateDictSource(sd, DEV), DEV, precision)
+    out = vae.decode(g["z"].to(DEV)).sample
+    torch.cuda.synchronize()
+    assert out.shape == g["out"].shape and torch.isfinite(out).all()
+    assert rel_l2(out, g["out"]) < tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_autoencoder_decode_vs_oracle(precision, tol):
+    """post_quant_conv + decoder, batch 3, non-square latent, weights shared through the state dict"""
+    cfg = ov.tiny_vae()
+    ovae = _oracle_vae(cfg)
+    z = torch.randn(3, 4, 16, 24, generator=torch.Generator().manual_seed(5))
+    ref = ovae.decode(z)
+    vae = AutoencoderKL(VaeConfig(**cfg.to_dict()), weights.StateDictSource(ovae.state_dict(), DEV), DEV, precision)
+    assert set(vae_decoder_param_shapes(vae.config)) == set(ovae.state_dict())
+    assert all(tuple(v.shape) == tuple(vae_decoder_param_shapes(vae.config)[k]) for k, v in ovae.state_dict().items())
+    out = vae.decode(z.to(DEV), return_dict=False)[0]
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < tol
+    with pytest.raises(ValueError):
+        vae.decode(torch.zeros(1, 3, 8, 8, device=DEV))
+
+
+@pytest.mark.parametrize("precision,min_psnr,preview_start", [("fp32", 60.0, 0.0), ("fp16", 40.0, 0.0), ("bf16", 40.0, 1.0)])
+def test_pipeline_decoded_image_psnr_vs_oracle(precision, min_psnr, preview_start):
+    """BASELINE config 1 end to end: denoising loop + VAE decode through the public API (output_type='pt') against the
+    oracle loop + oracle VAE on the same weights and seeds.  North star: decoded-image PSNR >= 40 dB."""
+    oc = ocfg.tiny()
+    alpha = 8.0
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=alpha)
+    vcfg = ov.tiny_vae()
+    ovae = _oracle_vae(vcfg)
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    kw = dict(num_inference_steps=2, guidance_scale=7.0, preview_start=preview_start)
+    ref_lat = opipe.restore_latents(
+        ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], generator=torch.Generator().manual_seed(42), **kw)
+    ref_img = ov.latents_to_image(ovae, ref_lat)
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = pcfg.ModelConfig(**oc.to_dict())
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=alpha / oc.lora_rank), DEV, precision)
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, precision)
+    vae = AutoencoderKL(VaeConfig(**vcfg.to_dict()), weights.StateDictSource(ovae.state_dict(), DEV), DEV, precision)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler(), vae=vae)
+    img = pipe(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+               pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+               ip_adapter_image_embeds=[inp["ip"]], previewer_scheduler=LCMSingleStepScheduler(),
+               generator=torch.Generator().manual_seed(42), output_type="pt", **kw).images
+    torch.cuda.synchronize()
+    assert img.shape == ref_img.shape == (1, 3, 128, 128)
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+    p = ov.psnr(img.cpu(), ref_img)
+    assert p >= min_psnr, f"{precision}: PSNR {p:.1f} dB"
+    arr = postprocess(torch.zeros(1, 3, 4, 4), "np")
+    assert arr.shape == (1, 4, 4, 3) and float(arr.mean()) == 0.5
+
+
+def test_pipeline_without_vae_rejects_image_output():
+    oc = ocfg.tiny()
+    ounet, oagg = build_oracle(oc, seed=0)
+    usd, _ = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = pcfg.ModelConfig(**oc.to_dict())
+    pipe = InstantIRPipeline(UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV), DEV, "fp32"),
+                             Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, "fp32"), DDPMScheduler())
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    with pytest.raises(ValueError):
+        pipe(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+             pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+             ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=1, preview_start=1.0, output_type="pt")

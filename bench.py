@@ -302,6 +302,35 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = res.numel() * res.element_size()
 
+    # ---- VAE decode (once per image): device time of vae.decode on the final latents and the e2e
+    # figure with it (output_type="pt": D2H of the decoded images instead of the latents)
+    vae_info = None
+    if world == 1 and not args.no_vae and wl != "config1":
+        from instantir_b200.vae import AutoencoderKL, VaeConfig, vae_decoder_param_shapes
+        from instantir_b200 import weights as _w
+
+        vcfg = VaeConfig()
+        vae = AutoencoderKL(vcfg, _w.RandomSource(vae_decoder_param_shapes(vcfg), dev, seed=2), dev, args.precision)
+        zl = loop.latents / vcfg.scaling_factor
+        vae.decode(zl)
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(3):
+            img = vae.decode(zl).sample
+        v1.record()
+        torch.cuda.synchronize()
+        dec_ms = v0.elapsed_time(v1) / 3
+        assert bool(torch.isfinite(img).all())
+        t0 = time.perf_counter()
+        himg = (vae.decode(res.to(dev) / vcfg.scaling_factor).sample / 2 + 0.5).clamp(0, 1).to("cpu")
+        dec_e2e_s = time.perf_counter() - t0
+        vae_info = {"decode_ms_per_batch": dec_ms, "images": B, "e2e_with_decode": n_images / (e2e_s + dec_e2e_s), "unit": "img/s",
+                    "d2h_bytes_per_image": himg.numel() * himg.element_size() // B,
+                    "note": "SDXL VAE decoder (49.5 M parameters, random-init), latent -> 8x image, eager launches"}
+        del vae, img, himg
+        torch.cuda.empty_cache()
+
     if rank == 0:
         # ---- roofline leg: CUDA events around every launch INSIDE the replayed CUDA graphs (event-record nodes
         # captured with the kernels), i.e. the per-kernel durations of the timed configuration itself, without
@@ -376,6 +405,7 @@ def run_ours(args):
             "e2e": {"value": n_images / e2e_s, "unit": "img/s", "h2d_bytes_per_step": h2d / STEPS_PER_IMAGE,
                     "d2h_bytes_per_step": d2h / STEPS_PER_IMAGE, "seconds_per_image_batch": e2e_s,
                     "note": "copies happen once per image (30 steps); bytes are per denoising step"},
+            "vae_decode": vae_info,
             "gpu_launches": int(launches),
             "roofline": roof,
             "step_tflops": (step_flops * B / (ms_per_step * 1e-3) / 1e12) if step_flops else None,
@@ -452,6 +482,7 @@ def main():
     ap.add_argument("--cfg-parallel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fp16", action="store_true", help="skip the fp16 comparison leg")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode leg (SURVEY §8 f1)")
     ap.add_argument("--agg-ahead", action="store_true", help="run Aggregator(t_{i+1}) beside the whole UNet(t_i) (previewer-off workloads)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="16-bit operand type of the timed run")
     args = ap.parse_args()

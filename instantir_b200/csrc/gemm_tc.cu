@@ -43,9 +43,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
+// Footprint variants (template parameter EW = epilogue warps):
+//   EW = 8: 8 epilogue warps, all 512 TMEM columns (two accumulator buffers), up to 227 KB of shared memory, one CTA/SM;
+//   EW = 4 ("half-SM"): 4 epilogue warps, 256 TMEM columns (one accumulator buffer), <= 113 KB, TWO CTAs per SM, so that
+//           GEMM CTAs of two streams, or a GEMM CTA and an attention CTA, can share an SM.  Chosen per
+//           launch for one-wave problems when IIR_GEMM_HALF=1.
+constexpr int ACC_STRIDE = 256;                 // TMEM columns between the two accumulator buffers
+constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }  // TMA warp + MMA warp + epilogue warps
+constexpr int smem_budget(int ew) { return ew == 4 ? 113 * 1024 : 227 * 1024; }
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 columns, XOR-swizzled
 constexpr int VEC_BYTES = 4096;        // tile bias + tile column sums, 2 x 256 floats each (double-buffered)
 constexpr float LN_S1_SCALE = 4294967296.f;  // 2^32: |row sum| < 2^31
@@ -112,10 +117,14 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int stile
   return c;
 }
 
-template <int PAIR, int CL, bool MMA2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int PAIR, int CL, bool MMA2, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), EW == 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   static_assert(!MMA2 || CL == 2, "cta_group::2 needs a 2-CTA cluster");
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  constexpr int TMEM_COLS = EW == 4 ? 256 : 512;
+  constexpr int NBUF = EW == 4 ? 1 : 2;        // accumulator buffers
+  constexpr int CH_STRIDE = 32 * (EW / 4);     // column distance between consecutive chunks of one epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -149,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], MMA2 ? 512 : 256);  // MMA2: both CTAs' epilogues arrive on the leader's
+      mbar_init(&tempty_bar[b], (MMA2 ? 2 : 1) * 32 * EW);  // MMA2: both CTAs' epilogues arrive on the leader's
     }
     fence_mbar_init();
   }
@@ -218,8 +227,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       uint32_t phase = 0;
       uint32_t acc_i = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
-        const uint32_t buf = acc_i & 1;
-        const uint32_t acc_phase = (acc_i >> 1) & 1;
+        const uint32_t buf = acc_i % NBUF;
+        const uint32_t acc_phase = (acc_i / NBUF) & 1;
         mbar_wait_sleep(&tempty_bar[buf], acc_phase ^ 1, 20000);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * ACC_STRIDE;
@@ -273,8 +282,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const int cc4 = lane & 7;                // coalesced phase: float4 column
     uint32_t acc_i = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++acc_i) {
-      const uint32_t buf = acc_i & 1;
-      const uint32_t acc_phase = (acc_i >> 1) & 1;
+      const uint32_t buf = acc_i % NBUF;
+      const uint32_t acc_phase = (acc_i / NBUF) & 1;
       TileCoord c = tile_coord<CL>(p, tile, rank);
       auto row_to_m = [&](int r) -> long long {  // output row of tile row r, or -1 when outside the matrix
         if (p.conv) {
@@ -300,12 +309,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       float* sb = s_bias + (acc_i & 1) * 256;
       float* sc = s_cs + (acc_i & 1) * 256;
       if (p.bias || p.ln_colsum) {
-        const int t = threadIdx.x - 64;  // 0..255 over the 8 epilogue warps
-        if (t < p.BN) {
+        for (int t = threadIdx.x - 64; t < p.BN; t += 32 * EW) {  // the epilogue warps' threads
           if (p.bias) sb[t] = (c.n0 + t < p.N) ? p.bias[c.n0 + t] : 0.f;
           if (p.ln_colsum) sc[t] = (c.n0 + t < p.N) ? p.ln_colsum[c.n0 + t] : 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       }
       // folded LayerNorm, consumer side: y = rstd * (x W'^T) - rstd * mean * colsum(W') + b'  (b' arrives as bias);
       // mean / rstd of this thread's row from the producer's partial sums
@@ -324,9 +332,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
       const int ncols = PAIR ? half : p.BN;  // accumulator columns that map to output columns
       const int nout0 = PAIR ? (c.n0 >> 1) : c.n0;
-      const int nchunks_w = ncols > chunk_par * 32 ? (ncols - chunk_par * 32 + 63) / 64 : 0;  // chunks of this warp
+      const int nchunks_w = ncols > chunk_par * 32 ? (ncols - chunk_par * 32 + CH_STRIDE - 1) / CH_STRIDE : 0;  // chunks of this warp
       auto prefetch = [&](int k) {
-        const int pc = chunk_par * 32 + 64 * k;
+        const int pc = chunk_par * 32 + CH_STRIDE * k;
         const int pcol = nout0 + pc + cc4 * 4;
         const bool ok = (pc + cc4 * 4 < ncols) && (pcol < n_out_total);
         uint8_t* slot = stg + (k % R) * EPI_STAGE_BYTES;
@@ -346,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
       for (int kc = 0; kc < nchunks_w; ++kc) {
-        const int cc = chunk_par * 32 + 64 * kc;
+        const int cc = chunk_par * 32 + CH_STRIDE * kc;
         uint8_t* slot = stg + (kc % R) * EPI_STAGE_BYTES;
         uint32_t r[32];
         uint32_t r2[32];
@@ -654,26 +662,41 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   }
 
   const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;
+  // half-SM variant: only for launches that are a single wave of CTAs anyway (one accumulator buffer: no epilogue /
+  // main-loop overlap between tiles of a CTA) and whose pipeline still gets >= 3 stages in 113 KB
+  static int half_env = -1;
+  if (half_env < 0) {
+    const char* e = getenv("IIR_GEMM_HALF");
+    half_env = e ? atoi(e) : 0;
+  }
+  int ew = 8;
+  if (half_env == 1 && p.tiles_m_cl * p.tiles_n * cl <= sm_count() &&
+      (smem_budget(4) - 1024 - 256 - VEC_BYTES - 4 * EPI_STAGE_BYTES) / stage_bytes >= 3)
+    ew = 4;
+  const int CH_STRIDE = 32 * (ew / 4), SMEM_BUDGET = smem_budget(ew), EW = ew;
+  const bool HALF_SM = ew == 4;
   // staging slots per epilogue warp: enough for this warp's chunks of the tile when an fp32 residual is
   // prefetched (at most 3), but never at the price of a shallow main-loop pipeline (measured: a CTA pair
   // wants >= 6 stages of 26 KB at K = 5120, one CTA >= 4 of 36 KB)
   int slots = 1;
   if (a->residual && a->res_dtype == IIR_F32) {
     const int ncols = a->pair ? a->bn / 2 : a->bn;
-    slots = (ncols + 63) / 64;
+    slots = (ncols + CH_STRIDE - 1) / CH_STRIDE;
     if (slots > 3) slots = 3;
     int want = mma2 ? 6 : 4;
     if (want > p.num_kb + 1) want = p.num_kb + 1;
-    while (slots > 1 && (227 * 1024 - 1024 - 256 - VEC_BYTES - 8 * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
+    if (HALF_SM) want = 3;
+    while (slots > 1 && (SMEM_BUDGET - 1024 - 256 - VEC_BYTES - EW * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
   }
   p.epi_slots = slots;
-  const int epi_bytes = 8 * slots * EPI_STAGE_BYTES;
-  int stages = (227 * 1024 - 1024 - 256 - VEC_BYTES - epi_bytes) / stage_bytes;
+  const int epi_bytes = EW * slots * EPI_STAGE_BYTES;
+  int stages = (SMEM_BUDGET - 1024 - 256 - VEC_BYTES - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + VEC_BYTES + epi_bytes;
-  if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
+  if (!HALF_SM && smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (each allocates all of TMEM)
+  IIR_REQUIRE(stages >= 2, "iir_gemm_tc: tile bn=%d does not fit the shared-memory budget of this build", a->bn);
 
   const int num_tiles = p.tiles_m_cl * p.tiles_n;  // super-tiles, one per cluster at a time
   int grid = (sm_count() / cl) * cl;
@@ -681,11 +704,14 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
 
   cudaError_t e;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH2(PAIRV, CLV, M2)                                                                          \
-  e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV, CLV, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                           (int)smem);                                                                    \
-  if (e == cudaSuccess)                                                                                   \
-    e = launch_cluster_pdl(gemm_tc_kernel<PAIRV, CLV, M2>, dim3(grid), dim3(GEMM_THREADS), smem, st, CLV, p);
+#define LAUNCH3(PAIRV, CLV, M2, EWV)                                                                            \
+  e = cudaFuncSetAttribute(gemm_tc_kernel<PAIRV, CLV, M2, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           (int)smem);                                                                           \
+  if (e == cudaSuccess)                                                                                          \
+    e = launch_cluster_pdl(gemm_tc_kernel<PAIRV, CLV, M2, EWV>, dim3(grid), dim3(gemm_threads(EWV)), smem, st, CLV, p);
+#define LAUNCH2(PAIRV, CLV, M2)         \
+  if (ew == 4) { LAUNCH3(PAIRV, CLV, M2, 4) } \
+  else { LAUNCH3(PAIRV, CLV, M2, 8) }
 #define LAUNCH(PAIRV)                                \
   if (mma2) { LAUNCH2(PAIRV, 2, true) }              \
   else if (cl == 4) { LAUNCH2(PAIRV, 4, false) }     \
@@ -697,6 +723,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   else { set_error("iir_gemm_tc: bad pair=%d", a->pair); return IIR_ERR_INVALID; }
 #undef LAUNCH
 #undef LAUNCH2
+#undef LAUNCH3
   if (e != cudaSuccess) {
     set_error("iir_gemm_tc: %s", cudaGetErrorString(e));
     return IIR_ERR_CUDA;

@@ -709,7 +709,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
                            (int)smem);                                                                           \
   if (e == cudaSuccess)                                                                                          \
     e = launch_cluster_pdl(gemm_tc_kernel<PAIRV, CLV, M2, EWV>, dim3(grid), dim3(gemm_threads(EWV)), smem, st, CLV, p);
-#define LAUNCH2(PAIRV, CLV, M2)         \
+#define LAUNCH2(PAIRV, CLV, M2)               \
   if (ew == 4) { LAUNCH3(PAIRV, CLV, M2, 4) } \
   else { LAUNCH3(PAIRV, CLV, M2, 8) }
 #define LAUNCH(PAIRV)                                \

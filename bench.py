@@ -260,10 +260,15 @@ def run_ours(args):
         sampler.start()
     launches0 = LaunchCounter.total()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:  # `ncu --profile-from-start off`: only the timed steps are profiled
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         loop.step((args.warmup + i) % n_sched)
     e1.record()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -482,6 +487,7 @@ def main():
     ap.add_argument("--cfg-parallel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fp16", action="store_true", help="skip the fp16 comparison leg")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode leg (SURVEY §8 f1)")
     ap.add_argument("--agg-ahead", action="store_true", help="run Aggregator(t_{i+1}) beside the whole UNet(t_i) (previewer-off workloads)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="16-bit operand type of the timed run")

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 5
+#define IIR_ABI_VERSION 6
 
 typedef enum {
   IIR_OK = 0,
@@ -101,6 +101,8 @@ typedef struct {
   void* ln_stats_zero;
   const float* ln_colsum;
   float ln_eps;
+  int conv_asym;        /* simt, stride 2 only: pad bottom/right only (diffusers Downsample2D(padding=0) of the VAE
+                           encoder: F.pad (0,1,0,1) then a pad-0 stride-2 conv); 0 = symmetric pad 1           */
 } iir_gemm_args;
 
 /* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */
@@ -194,9 +196,10 @@ int iir_concat_inject(const void* h, int h_dtype, int C1, const void* rh, int rh
 /* nearest 2x upsample NHWC (module/min_sdxl.py:617) with dtype conversion                   */
 int iir_upsample2x(const void* x, int x_dtype, void* out, int out_dtype, int n_img, int H, int W,
                    int C, void* stream);
-/* 3x3 stride-2 pad-1 patch gather -> [n_img*Ho*Wo, 9*C] (Downsample2D, module/min_sdxl.py:598-606) */
+/* 3x3 stride-2 patch gather -> [n_img*Ho*Wo, 9*C] (Downsample2D, module/min_sdxl.py:598-606); asym = 0: pad 1 on
+ * every side; asym = 1: pad bottom/right only (the VAE encoder's Downsample2D(padding=0), H and W even)          */
 int iir_im2col3x3_s2(const void* x, int x_dtype, void* out, int out_dtype, int n_img, int H, int W,
-                     int C, void* stream);
+                     int C, int asym, void* stream);
 /* strided 2-D copy/cast: out[r, c] = in[r*ld_in + c]                                        */
 int iir_cast2d(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
                int64_t ld_out, int64_t rows, int cols, void* stream);
@@ -231,6 +234,11 @@ int iir_cfg_ddpm_step(const void* eps_uncond, const void* eps_cond, int eps_dtyp
 /* add_noise (lcm_single_step_scheduler.py:492-513): out = sqrt(abar)*x0 + sqrt(1-abar)*noise */
 int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n, float alpha_prod_t,
                   void* stream);
+/* DiagonalGaussianDistribution.sample of the VAE encoder (module/diffusers_vae/vae.py, used at
+ * pipelines/sdxl_instantir.py:1375-1376): moments [n_samples, 2*half] = (mean | logvar) per sample,
+ * out = (mean + exp(0.5*clamp(logvar, -30, 20)) * noise) * scale; noise NULL = the distribution's mode.        */
+int iir_gaussian_sample(const float* moments, const float* noise, float* out, int64_t n_samples, int64_t half,
+                        float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
@@ -26,7 +26,7 @@ SYMBOLS = [
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add",
     "iir_timestep_embedding", "iir_linear_small",
-    "iir_lcm_step", "iir_cfg_ddpm_step", "iir_add_noise",
+    "iir_lcm_step", "iir_cfg_ddpm_step", "iir_add_noise", "iir_gaussian_sample",
 ]
 
 
@@ -48,6 +48,7 @@ class GemmArgs(C.Structure):
         ("ld_rowvec", C.c_int64),
         ("ln_stats_out", C.c_void_p), ("ln_out16", C.c_void_p), ("ld_ln_out16", C.c_int64),
         ("ln_stats_in", C.c_void_p), ("ln_stats_zero", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
+        ("conv_asym", C.c_int),
     ]
 
 
@@ -97,12 +98,13 @@ def _declare(lib):
     lib.iir_softmax_rows.argtypes = [vp, i64, vp, i, i64, i, i, f, vp]
     lib.iir_concat_inject.argtypes = [vp, i, i, vp, i, vp, i, i, vp, i, vp, i, vp, i, i64, vp]
     lib.iir_upsample2x.argtypes = [vp, i, vp, i, i, i, i, i, vp]
-    lib.iir_im2col3x3_s2.argtypes = [vp, i, vp, i, i, i, i, i, vp]
+    lib.iir_im2col3x3_s2.argtypes = [vp, i, vp, i, i, i, i, i, i, vp]
     lib.iir_cast2d.argtypes = [vp, i, i64, vp, i, i64, i64, i, vp]
     lib.iir_silu.argtypes = [vp, i, vp, i, i64, vp]
     lib.iir_add.argtypes = [vp, i, vp, i, vp, i, i64, vp]
     lib.iir_timestep_embedding.argtypes = [vp, i, i, vp, i, vp]
     lib.iir_linear_small.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, vp]
+    lib.iir_gaussian_sample.argtypes = [vp, vp, vp, i64, i64, f, vp]
     lib.iir_lcm_step.argtypes = [vp, i, vp, vp, i64, f, f, f, vp]
     lib.iir_cfg_ddpm_step.argtypes = [vp, vp, i, vp, vp, vp, vp, i64, f, f, f, f, f, vp]
     lib.iir_add_noise.argtypes = [vp, vp, vp, i64, f, vp]

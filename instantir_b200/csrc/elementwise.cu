@@ -72,7 +72,7 @@ upsample2x_kernel(const void* x, int x_bf, void* out, int out_bf, int n_img, int
 
 __global__ void __launch_bounds__(256)
 im2col3x3_s2_kernel(const void* x, int x_bf, void* out, int out_bf, int n_img, int H, int W, int C,
-                    int Ho, int Wo) {
+                    int Ho, int Wo, int lead) {
   const int cv = C >> 2;
   const long long total = static_cast<long long>(n_img) * Ho * Wo * 9 * cv;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
@@ -84,7 +84,7 @@ im2col3x3_s2_kernel(const void* x, int x_bf, void* out, int out_bf, int n_img, i
     int oy = static_cast<int>((pix / Wo) % Ho);
     long long n = pix / (static_cast<long long>(Wo) * Ho);
     int ky = tap / 3, kx = tap - ky * 3;
-    int y = oy * 2 + ky - 1, xx = ox * 2 + kx - 1;
+    int y = oy * 2 + ky - lead, xx = ox * 2 + kx - lead;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < H && xx >= 0 && xx < W) a = ld4_any(x, x_bf, ((n * H + y) * W + xx) * C + v * 4);
     st4_any(out, out_bf, (pix * 9 + tap) * C + v * 4, a);
@@ -174,13 +174,14 @@ extern "C" int iir_upsample2x(const void* x, int x_dtype, void* out, int out_dty
 }
 
 extern "C" int iir_im2col3x3_s2(const void* x, int x_dtype, void* out, int out_dtype, int n_img,
-                                int H, int W, int C, void* stream) {
+                                int H, int W, int C, int asym, void* stream) {
   IIR_REQUIRE(x && out && n_img > 0 && H > 0 && W > 0 && C % 4 == 0, "iir_im2col3x3_s2: bad shape");
+  IIR_REQUIRE(!asym || (H % 2 == 0 && W % 2 == 0), "iir_im2col3x3_s2: bottom/right-only padding needs even H, W");
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long work = 9LL * n_img * Ho * Wo * (C / 4);
   im2col3x3_s2_kernel<<<grid_for(work), 256, 0, st>>>(x, x_dtype == IIR_H16, out,
-                                                      out_dtype == IIR_H16, n_img, H, W, C, Ho, Wo);
+                                                      out_dtype == IIR_H16, n_img, H, W, C, Ho, Wo, asym ? 0 : 1);
   count_launch();
   return check_launch("iir_im2col3x3_s2");
 }

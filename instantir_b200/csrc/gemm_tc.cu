@@ -562,7 +562,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   bool mma2 = false;  // cta_group::2 CTA pairs
   CUresult cr;
   if (a->conv) {
-    IIR_REQUIRE(a->conv == 3 && a->stride == 1 && a->up2 == 0,
+    IIR_REQUIRE(a->conv == 3 && a->stride == 1 && a->up2 == 0 && !a->conv_asym,
                 "iir_gemm_tc: conv mode supports 3x3 stride 1 only");
     IIR_REQUIRE(a->Cin % BK == 0 && a->K == 9 * a->Cin, "iir_gemm_tc: conv needs Cin%%64==0, K==9*Cin");
     IIR_REQUIRE(a->M == a->n_img * a->H * a->W, "iir_gemm_tc: conv M mismatch");

@@ -64,6 +64,20 @@ add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
   }
 }
 
+// DiagonalGaussianDistribution.sample (module/diffusers_vae/vae.py: mean, logvar = moments.chunk(2, dim=1);
+// logvar clamped to [-30, 20]; sample = mean + exp(0.5 logvar) * noise), times `scale`; NCHW, per sample the first
+// `half` elements of `moments` are the mean and the next `half` the log-variance
+__global__ void __launch_bounds__(256)
+gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float* __restrict__ out,
+                       long long total, long long half, float scale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long b = i / half, r = i - b * half;
+    const float mean = moments[b * 2 * half + r];
+    const float logvar = fminf(fmaxf(moments[b * 2 * half + half + r], -30.0f), 20.0f);
+    out[i] = (mean + expf(0.5f * logvar) * (noise ? noise[i] : 0.0f)) * scale;
+  }
+}
+
 int grid_for4(long long n4) {
   long long b = (n4 + 255) / 256;
   long long cap = 8LL * sm_count();
@@ -118,4 +132,14 @@ extern "C" int iir_add_noise(const float* x0, const float* noise, float* out, in
                                                      sqrtf(1.0f - alpha_prod_t));
   count_launch();
   return check_launch("iir_add_noise");
+}
+
+extern "C" int iir_gaussian_sample(const float* moments, const float* noise, float* out, int64_t n_samples,
+                                   int64_t half, float scale, void* stream) {
+  IIR_REQUIRE(moments && out && n_samples > 0 && half > 0, "iir_gaussian_sample: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n_samples) * half;
+  gaussian_sample_kernel<<<grid_for4(total), 256, 0, st>>>(moments, noise, out, total, static_cast<long long>(half), scale);
+  count_launch();
+  return check_launch("iir_gaussian_sample");
 }

@@ -12,7 +12,7 @@ struct GemmSimtParams {
   const void* w;
   int M, N, K;
   long long lda;
-  int conv, n_img, H, W, Cin, stride, up2, Ho, Wo;
+  int conv, n_img, H, W, Cin, stride, up2, Ho, Wo, lead;
   const float* bias;
   const float* rowvec;
   long long ld_rowvec;
@@ -34,7 +34,7 @@ __device__ __forceinline__ float load_a(const GemmSimtParams& p, int m, int k) {
   int n = m / hw;
   int r = m - n * hw;
   int oy = r / p.Wo, ox = r - oy * p.Wo;
-  int y = oy * p.stride + ky - 1, x = ox * p.stride + kx - 1;
+  int y = oy * p.stride + ky - p.lead, x = ox * p.stride + kx - p.lead;
   if (y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.0f;
   int sh = p.H, sw = p.W;
   if (p.up2) { y >>= 1; x >>= 1; sh >>= 1; sw >>= 1; }
@@ -482,6 +482,9 @@ extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
     IIR_REQUIRE(a->conv == 3 && (a->stride == 1 || a->stride == 2), "iir_gemm_simt: 3x3 s1/s2 only");
     IIR_REQUIRE(a->K == 9 * a->Cin, "iir_gemm_simt: K must be 9*Cin");
     p.n_img = a->n_img; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.stride = a->stride; p.up2 = a->up2;
+    IIR_REQUIRE(!a->conv_asym || (a->stride == 2 && a->H % 2 == 0 && a->W % 2 == 0 && !a->up2),
+                "iir_gemm_simt: conv_asym (pad bottom/right only) needs stride 2 and even H, W");
+    p.lead = a->conv_asym ? 0 : 1;
     p.Ho = (a->H + 2 - 3) / a->stride + 1;
     p.Wo = (a->W + 2 - 3) / a->stride + 1;
     IIR_REQUIRE(a->M == a->n_img * p.Ho * p.Wo, "iir_gemm_simt: conv M mismatch (M=%d, expect %d)",

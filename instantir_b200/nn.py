@@ -270,8 +270,9 @@ class SmallLinearBank:
 class Conv3x3:
     """3x3 pad-1 convolution as implicit GEMM (module/min_sdxl.py:246-260,601-618)."""
 
-    def __init__(self, rt, src, name, stride=1):
-        self.rt, self.stride = rt, stride
+    def __init__(self, rt, src, name, stride=1, asym=False):
+        """asym (stride 2 only): pad bottom/right only — diffusers Downsample2D(padding=0) of the VAE encoder"""
+        self.rt, self.stride, self.asym = rt, stride, asym
         self.w = _load_w(rt, src, name, _conv_to_gemm)
         self.b = _bias(src, name)
         self.Cout = self.w.base.shape[0]
@@ -286,7 +287,8 @@ class Conv3x3:
         kw = dict(M=M, N=self.Cout, K=9 * self.Cin, bias=self.b, rowvec=rowvec, rows_per_sample=Ho * Wo,
                   residual=residual, act=act)
         if not rt.tc:
-            ops.gemm(x.t, self.w.get(), out, conv=dict(n_img=x.n, H=H, W=W, Cin=self.Cin, stride=self.stride, up2=int(up2)),
+            ops.gemm(x.t, self.w.get(), out, conv=dict(n_img=x.n, H=H, W=W, Cin=self.Cin, stride=self.stride, up2=int(up2),
+                                                       asym=int(self.asym)),
                      tc=False, **kw)
         else:
             src = x
@@ -298,7 +300,7 @@ class Conv3x3:
                 pass
             if self.stride == 2:
                 cols = rt.empty(M, 9 * self.Cin)
-                ops.im2col3x3_s2(src.t, cols, n_img=x.n, H=H, W=W, C=self.Cin)
+                ops.im2col3x3_s2(src.t, cols, n_img=x.n, H=H, W=W, C=self.Cin, asym=self.asym)
                 ops.gemm(cols, self.w.get(), out, tc=True, **kw)
             else:
                 a = src.t

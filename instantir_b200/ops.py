@@ -173,6 +173,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         g.n_img, g.H, g.W, g.Cin = conv["n_img"], conv["H"], conv["W"], conv["Cin"]
         g.stride = conv.get("stride", 1)
         g.up2 = conv.get("up2", 0)
+        g.conv_asym = int(conv.get("asym", 0))
     g.bias = _p(_f32c(bias, "bias"))
     rowvec, g.ld_rowvec = _f32rows(rowvec, "rowvec")
     g.rowvec = _p(rowvec)
@@ -329,10 +330,11 @@ def upsample2x(x, out, *, n_img: int, H: int, W: int, C: int):
     return out
 
 
-def im2col3x3_s2(x, out, *, n_img: int, H: int, W: int, C: int):
+def im2col3x3_s2(x, out, *, n_img: int, H: int, W: int, C: int, asym: bool = False):
+    """asym: pad bottom/right only (the VAE encoder's Downsample2D(padding=0)) instead of pad 1 on every side"""
     lib = _L(x, out)
     with _Prof("im2col3x3_s2", bytes=float(n_img) * H * W * C * (x.element_size() + 2.25 * out.element_size())):
-        _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, _stream()),
+        _lib.check(lib.iir_im2col3x3_s2(_p(x), _dt(x), _p(out), _dt(out), n_img, H, W, C, int(asym), _stream()),
                    "iir_im2col3x3_s2", lib)
     return out
 
@@ -412,4 +414,18 @@ def softmax_rows(x: torch.Tensor, out: torch.Tensor, *, scale: float):
     with _Prof("softmax_rows", bytes=float(rows) * n * (3 * 4 + out.element_size())):
         _lib.check(lib.iir_softmax_rows(_p(x), x.stride(0), _p(out), _dt(out), out.stride(0), rows, n, float(scale), _stream()),
                    "iir_softmax_rows", lib)
+    return out
+
+
+def gaussian_sample(moments: torch.Tensor, noise, out: torch.Tensor, *, scale: float = 1.0):
+    """moments [B, 2L, h, w] fp32 (mean | logvar) -> out [B, L, h, w] = (mean + exp(0.5 clamp(logvar)) * noise) * scale;
+    noise None = the mode."""
+    lib = _L()
+    B = moments.shape[0]
+    half = moments[0].numel() // 2
+    _f32c(moments, "moments"), _f32c(out, "out")
+    if noise is not None:
+        _f32c(noise, "noise")
+    _lib.check(lib.iir_gaussian_sample(_p(moments), _p(noise), _p(out), B, half, float(scale), _stream()),
+               "iir_gaussian_sample", lib)
     return out

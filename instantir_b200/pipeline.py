@@ -116,8 +116,12 @@ class InstantIRPipeline:
         if negative_prompt_embeds is not None and prompt_embeds.shape != negative_prompt_embeds.shape:
             raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed directly, "
                              f"but got {prompt_embeds.shape} != {negative_prompt_embeds.shape}.")
-        if not torch.is_tensor(image) or image.ndim != 4 or image.shape[1] != self.unet.cfg.in_channels:
-            raise TypeError("`image` must be a 4-channel latent tensor [B,4,h,w] (VAE encode is outside this build's scope)")
+        if not torch.is_tensor(image) or image.ndim != 4:
+            raise TypeError("`image` must be a tensor: a 4-channel LQ latent [B,4,h,w] or, with a VAE, an image [B,3,H,W] in [-1,1]")
+        if image.shape[1] != self.unet.cfg.in_channels and (self.vae is None or getattr(self.vae, "encoder", None) is None
+                                                             or image.shape[1] != self.vae.config.in_channels):
+            raise TypeError("`image` must be a 4-channel latent tensor [B,4,h,w] (pass vae=AutoencoderKL(...) with encoder "
+                            "weights to give a 3-channel image instead)")
         if ip_adapter_image_embeds is None:
             raise ValueError("Provide `ip_adapter_image_embeds` (DINOv2 tokens [2,B,S,D] or a list holding that tensor).")
         if control_guidance_start >= control_guidance_end:
@@ -171,6 +175,10 @@ class InstantIRPipeline:
         do_cfg = guidance_scale > 1.0
         f32 = dict(device=dev, dtype=torch.float32)
         image = image.to(**f32).contiguous()
+        if image.shape[1] != unet.cfg.in_channels:
+            # pipelines/sdxl_instantir.py:1370-1376: image -> vae.encode(...).latent_dist.sample() * scaling_factor
+            # (the reference draws this sample from torch's global RNG; here from `generator`, before any other draw)
+            image = self.vae.encode(image).latent_dist.sample(generator, scale=self.vae.config.scaling_factor)
         B, _, h, w = image.shape
         H_px, W_px = height or h * 8, width or w * 8
         ts, num_inference_steps = retrieve_timesteps(sched, num_inference_steps, dev, timesteps)

@@ -1,5 +1,6 @@
-"""VAE decode on the sm_100a kernels (the first "next" row): the once-per-image
-``vae.decode(latents / scaling_factor)`` of ``pipelines/sdxl_instantir.py:1670-1704``.
+"""VAE encode / decode on the sm_100a kernels (the first "next" row): the once-per-image
+``vae.encode(image).latent_dist.sample() * scaling_factor`` of ``pipelines/sdxl_instantir.py:1370-1376`` and
+``vae.decode(latents / scaling_factor)`` of ``:1670-1704``.
 
 ``AutoencoderKL.decode(z, return_dict)`` / ``.config.scaling_factor`` / ``.config.force_upcast`` mirror
 ``module/diffusers_vae/autoencoder_kl.py:270-300``; the decoder follows ``module/diffusers_vae/vae.py:185-350``
@@ -31,6 +32,42 @@ class VaeConfig(SimpleNamespace):
         super().__init__(in_channels=in_channels, out_channels=out_channels, latent_channels=latent_channels,
                          block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
                          norm_num_groups=norm_num_groups, scaling_factor=scaling_factor, force_upcast=force_upcast)
+
+
+def vae_param_shapes(cfg) -> dict:
+    """{state-dict key: shape} of the whole AutoencoderKL (encoder, quant_conv, post_quant_conv, decoder)."""
+    d = dict(vae_decoder_param_shapes(cfg))
+    ch, L = cfg.block_out_channels, cfg.latent_channels
+
+    def conv(p, co, ci, k):
+        d[p + ".weight"], d[p + ".bias"] = (co, ci, k, k), (co,)
+
+    def norm(p, c):
+        d[p + ".weight"], d[p + ".bias"] = (c,), (c,)
+
+    def resnet(p, ci, co):
+        norm(p + ".norm1", ci); conv(p + ".conv1", co, ci, 3); norm(p + ".norm2", co); conv(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv(p + ".conv_shortcut", co, ci, 1)
+
+    conv("encoder.conv_in", ch[0], cfg.in_channels, 3)
+    out = ch[0]
+    for i in range(len(ch)):
+        prev, out = out, ch[i]
+        for j in range(cfg.layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else out, out)
+        if i != len(ch) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", out, out, 3)
+    resnet("encoder.mid_block.resnets.0", ch[-1], ch[-1])
+    resnet("encoder.mid_block.resnets.1", ch[-1], ch[-1])
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", ch[-1])
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        d[f"{a}.{n}.weight"], d[f"{a}.{n}.bias"] = (ch[-1], ch[-1]), (ch[-1],)
+    norm("encoder.conv_norm_out", ch[-1])
+    conv("encoder.conv_out", 2 * L, ch[-1], 3)
+    conv("quant_conv", 2 * L, 2 * L, 1)
+    return d
 
 
 def vae_decoder_param_shapes(cfg) -> dict:
@@ -139,6 +176,52 @@ class _MidAttention:
         return FMap(out, x.n, x.H, x.W, C)
 
 
+class Encoder:
+    """module/diffusers_vae/vae.py:46-182: conv_in -> DownEncoderBlock2D x4 (resnets, then a stride-2 conv padded
+    bottom/right only) -> UNetMidBlock2D -> GroupNorm -> SiLU -> conv_out (2 x latent channels)."""
+
+    def __init__(self, rt: Runtime, src, cfg, p="encoder"):
+        self.rt, self.cfg = rt, cfg
+        ch, g = cfg.block_out_channels, cfg.norm_num_groups
+        self.conv_in_w = src.get(p + ".conv_in.weight").permute(0, 2, 3, 1).contiguous().float()
+        self.conv_in_b = src.get(p + ".conv_in.bias").contiguous().float()
+        self.down_blocks = []
+        out = ch[0]
+        for i in range(len(ch)):
+            prev, out = out, ch[i]
+            resnets = [_Resnet(rt, src, f"{p}.down_blocks.{i}.resnets.{j}", prev if j == 0 else out, out, g)
+                       for j in range(cfg.layers_per_block)]
+            down = Conv3x3(rt, src, f"{p}.down_blocks.{i}.downsamplers.0.conv", stride=2, asym=True) if i != len(ch) - 1 else None
+            self.down_blocks.append((resnets, down))
+        self.mid = [_Resnet(rt, src, p + ".mid_block.resnets.0", ch[-1], ch[-1], g),
+                    _MidAttention(rt, src, p + ".mid_block.attentions.0", ch[-1], g),
+                    _Resnet(rt, src, p + ".mid_block.resnets.1", ch[-1], ch[-1], g)]
+        self.conv_norm_out = GroupNorm(rt, src, p + ".conv_norm_out", ch[-1], g, 1e-6)
+        self.conv_out = Conv3x3(rt, src, p + ".conv_out")
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, 3, H, W] fp32 in [-1, 1] -> [B, 2*latent, H/8, W/8] fp32 (NCHW view of NHWC memory)."""
+        rt, cfg = self.rt, self.cfg
+        B, Ci, H, W = x.shape
+        n_down = len(cfg.block_out_channels) - 1
+        if H % (1 << n_down) or W % (1 << n_down):
+            raise ValueError(f"image size {H}x{W} must be a multiple of {1 << n_down}")
+        c0 = cfg.block_out_channels[0]
+        h = rt.stream(B * H * W, c0)
+        ops.conv3x3_direct(x.contiguous(), self.conv_in_w, self.conv_in_b, h, in_nchw=True, out_nchw=False,
+                           n_img=B, H=H, W=W, Cin=Ci, Cout=c0)
+        h = FMap(h, B, H, W, c0)
+        for resnets, down in self.down_blocks:
+            for r in resnets:
+                h = r(h)
+            if down is not None:
+                h = down(h, out_dtype=torch.float32)
+        for m in self.mid:
+            h = m(h)
+        y = self.conv_norm_out(h, silu=True)
+        return self.conv_out(y, out_dtype=torch.float32).nchw()
+
+
 class Decoder:
     def __init__(self, rt: Runtime, src, cfg, p="decoder"):
         self.rt, self.cfg = rt, cfg
@@ -192,8 +275,27 @@ class Decoder:
         return img[:, :self.n_out]
 
 
+class DiagonalGaussianDistribution:
+    """module/diffusers_vae/vae.py DiagonalGaussianDistribution over encoder moments [B, 2L, h, w] (mean | logvar):
+    ``sample(generator)`` = mean + exp(0.5 clamp(logvar, -30, 20)) * noise, ``mode()`` = mean."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.parameters = moments.contiguous()
+        self.shape = (moments.shape[0], moments.shape[1] // 2) + tuple(moments.shape[2:])
+
+    def sample(self, generator=None, scale: float = 1.0) -> torch.Tensor:
+        from .schedulers import _randn
+
+        noise = _randn(self.shape, generator, self.parameters.device)
+        return ops.gaussian_sample(self.parameters, noise, torch.empty(self.shape, device=self.parameters.device), scale=scale)
+
+    def mode(self) -> torch.Tensor:
+        return ops.gaussian_sample(self.parameters, None, torch.empty(self.shape, device=self.parameters.device))
+
+
 class AutoencoderKL:
-    """decode half of the reference's AutoencoderKL (the pipeline only decodes inside the scope of row f1)."""
+    """the reference's AutoencoderKL as the pipeline uses it: ``encode(x).latent_dist.sample()`` and ``decode(z)``.
+    A weight source without ``encoder.*`` keys gives a decode-only model."""
 
     def __init__(self, cfg, source, device="cuda", precision="bf16"):
         self.config = cfg if isinstance(cfg, VaeConfig) else VaeConfig(**(cfg if isinstance(cfg, dict) else cfg.to_dict()))
@@ -206,6 +308,29 @@ class AutoencoderKL:
         self.pq_b = source.get("post_quant_conv.bias").contiguous().float()
         self.decoder = Decoder(self.rt, source, self.config)
         self.dtype = self.rt.act_dtype
+        self.encoder = None
+        if source.has("encoder.conv_in.weight"):
+            self.encoder = Encoder(self.rt, source, self.config)
+            w = source.get("quant_conv.weight").float().reshape(2 * L, 2 * L)
+            self.q_w = torch.zeros(2 * L, 3, 3, 2 * L, device=w.device)
+            self.q_w[:, 1, 1, :] = w
+            self.q_b = source.get("quant_conv.bias").contiguous().float()
+
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """module/diffusers_vae/autoencoder_kl.py:236-268: encoder -> quant_conv -> DiagonalGaussianDistribution."""
+        if self.encoder is None:
+            raise ValueError("this AutoencoderKL was built from a weight source without 'encoder.*' tensors")
+        if x.ndim != 4 or x.shape[1] != self.config.in_channels:
+            raise ValueError(f"expected images [B, {self.config.in_channels}, H, W], got {tuple(x.shape)}")
+        x = x.to(device=self.rt.device, dtype=torch.float32).contiguous()
+        h = self.encoder(x).contiguous()  # NHWC memory -> NCHW for the 1x1 quant_conv
+        B, C2, hh, ww = h.shape
+        moments = torch.empty(B, C2, hh, ww, device=self.rt.device, dtype=torch.float32)
+        ops.conv3x3_direct(h, self.q_w, self.q_b, moments, in_nchw=True, out_nchw=True, n_img=B, H=hh, W=ww, Cin=C2, Cout=C2)
+        dist = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (dist,)
+        return SimpleNamespace(latent_dist=dist)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
         """module/diffusers_vae/autoencoder_kl.py:270-300: post_quant_conv then the decoder."""

@@ -1,4 +1,4 @@
-"""CPU fp32 restatement of the VAE decode the pipeline runs once per image — TEST
+"""CPU fp32 restatement of the VAE encode / decode the pipeline runs once per image — TEST
 INFRASTRUCTURE ONLY (see oracle/__init__.py): imported by tests/, tests/golden/ and bench.py's CPU legs.
 
 Follows the reference's vendored decoder plumbing ``module/diffusers_vae/vae.py:185-350`` (Decoder:
@@ -9,10 +9,12 @@ conv_in -> UNetMidBlock2D -> UpDecoderBlock2D x4 -> GroupNorm -> SiLU -> conv_ou
 The blocks themselves live in ``diffusers==0.28.1`` (``models/unets/unet_2d_blocks.py``, ``models/resnet.py``,
 ``models/upsampling.py``, ``models/attention_processor.py``), which is absent from /root/reference: they are
 restated here from their published definitions.  Pinning (tests/golden/make_golden_vae.py):
-  * Decoder.forward runs VERBATIM from the reference file over these blocks -> plumbing pinned;
+  * Decoder.forward and Encoder.forward (module/diffusers_vae/vae.py:46-182) run VERBATIM from the reference file
+    over these blocks, DiagonalGaussianDistribution verbatim -> plumbing and sampling pinned;
   * the mid-block attention arithmetic is the reference's own ``AttnProcessor2_0``
     (module/ip_adapter/attention_processor.py:337-414, 4-D input + group_norm + residual branch) -> pinned;
-  * ResnetBlock2D (temb=None) / Upsample2D arithmetic: parity unpinned (no reference source or vectors).
+  * ResnetBlock2D (temb=None) / Upsample2D / Downsample2D(padding=0) arithmetic: parity unpinned (no reference
+    source or vectors).
 """
 from __future__ import annotations
 
@@ -132,6 +134,65 @@ class UpDecoderBlock2D(nn.Module):
         return x
 
 
+class Downsample2D(nn.Module):
+    """diffusers Downsample2D(use_conv=True, padding=0) as DownEncoderBlock2D builds it: F.pad (0, 1, 0, 1) then a
+    stride-2, pad-0 3x3 conv (named `conv` in the checkpoint)."""
+
+    def __init__(self, C):
+        super().__init__()
+        self.conv = nn.Conv2d(C, C, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class DownEncoderBlock2D(nn.Module):
+    def __init__(self, num_layers, c_in, c_out, add_downsample, groups, eps=1e-6):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(c_in if i == 0 else c_out, c_out, groups, eps) for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(c_out)]) if add_downsample else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x, None)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+        return x
+
+
+class Encoder(nn.Module):
+    """module/diffusers_vae/vae.py:46-182 (double_z, mid-block attention)."""
+
+    def __init__(self, cfg: "VaeConfig"):
+        super().__init__()
+        ch, g = cfg.block_out_channels, cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.in_channels, ch[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        out = ch[0]
+        for i in range(len(ch)):
+            prev, out = out, ch[i]
+            self.down_blocks.append(DownEncoderBlock2D(cfg.layers_per_block, prev, out, i != len(ch) - 1, g))
+        self.mid_block = UNetMidBlock2D(ch[-1], g)
+        self.conv_norm_out = nn.GroupNorm(g, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], 2 * cfg.latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for b in self.down_blocks:
+            x = b(x)
+        x = self.mid_block(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+def gaussian_sample(moments, noise=None):
+    """DiagonalGaussianDistribution (module/diffusers_vae/vae.py): mean + exp(0.5 clamp(logvar, -30, 20)) * noise;
+    noise None = mode()."""
+    mean, logvar = moments.chunk(2, dim=1)
+    if noise is None:
+        return mean
+    return mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise
+
+
 class Decoder(nn.Module):
     """module/diffusers_vae/vae.py:185-350 (norm_type 'group', no latent_embeds)."""
 
@@ -164,10 +225,31 @@ class AutoencoderKLDecoder(nn.Module):
         self.cfg = cfg
         self.post_quant_conv = nn.Conv2d(cfg.latent_channels, cfg.latent_channels, 1)
         self.decoder = Decoder(cfg)
+        self._init_encoder(cfg)
+
+    def _init_encoder(self, cfg):
+        pass
 
     def decode(self, z):
         """module/diffusers_vae/autoencoder_kl.py:270-281"""
         return self.decoder(self.post_quant_conv(z))
+
+
+class AutoencoderKL(AutoencoderKLDecoder):
+    """encode + decode: adds 'encoder.*' and 'quant_conv.*' (module/diffusers_vae/autoencoder_kl.py:92-113)."""
+
+    def _init_encoder(self, cfg):
+        self.encoder = Encoder(cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+
+    def encode_moments(self, x):
+        """module/diffusers_vae/autoencoder_kl.py:236-268: encoder then quant_conv -> (mean | logvar)"""
+        return self.quant_conv(self.encoder(x))
+
+
+def image_to_latents(vae: "AutoencoderKL", image: torch.Tensor, noise=None) -> torch.Tensor:
+    """pipelines/sdxl_instantir.py:1375-1376: vae.encode(image).latent_dist.sample() * scaling_factor"""
+    return gaussian_sample(vae.encode_moments(image), noise) * vae.cfg.scaling_factor
 
 
 def latents_to_image(vae: AutoencoderKLDecoder, latents: torch.Tensor) -> torch.Tensor:

@@ -1,5 +1,5 @@
-"""Generate tests/golden/vae_decoder.pt by running the REFERENCE's vendored ``Decoder``
-(module/diffusers_vae/vae.py:185-350) verbatim in the authoring container (needs /root/reference).
+"""Generate tests/golden/vae_decoder.pt and vae_encoder.pt by running the REFERENCE's vendored ``Decoder`` /
+``Encoder`` / ``DiagonalGaussianDistribution`` (module/diffusers_vae/vae.py:46-350) verbatim in the authoring container (needs /root/reference).
 
     python tests/golden/make_golden_vae.py [--ref /root/reference]
 
@@ -63,8 +63,12 @@ def install_vae_stub():
         assert up_block_type == "UpDecoderBlock2D" and temb_channels is None
         return ov.UpDecoderBlock2D(num_layers, in_channels, out_channels, add_upsample, resnet_groups, resnet_eps)
 
-    blk.UNetMidBlock2D, blk.get_up_block = UNetMidBlock2D, get_up_block
-    blk.get_down_block = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("encoder not exercised"))
+    def get_down_block(down_block_type, num_layers, in_channels, out_channels, add_downsample, resnet_eps,
+                       downsample_padding, resnet_act_fn, resnet_groups, attention_head_dim, temb_channels):
+        assert down_block_type == "DownEncoderBlock2D" and temb_channels is None and downsample_padding == 0
+        return ov.DownEncoderBlock2D(num_layers, in_channels, out_channels, add_downsample, resnet_groups, resnet_eps)
+
+    blk.UNetMidBlock2D, blk.get_up_block, blk.get_down_block = UNetMidBlock2D, get_up_block, get_down_block
     blk.AutoencoderTinyBlock = type("AutoencoderTinyBlock", (), {})
 
 
@@ -92,6 +96,22 @@ def main():
     torch.save({"cfg": cfg.to_dict(), "seed": 61, "checksum": checksum(dec), "names": sorted(k for k, _ in dec.named_parameters()),
                 "z": z, "out": out}, os.path.join(HERE, "vae_decoder.pt"))
     print("vae_decoder.pt", tuple(out.shape), float(out.abs().mean()))
+
+    enc = rv.Encoder(in_channels=cfg.in_channels, out_channels=cfg.latent_channels,
+                     down_block_types=("DownEncoderBlock2D",) * len(cfg.block_out_channels),
+                     block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                     norm_num_groups=cfg.norm_num_groups, act_fn="silu", double_z=True)
+    seeded_init(enc, 63)
+    x = rnd(2, cfg.in_channels, 64, 48, seed=64)
+    h = enc(x)
+    moments = rnd(2, 2 * cfg.latent_channels, 6, 6, seed=65) * 3.0
+    noise = rnd(2, cfg.latent_channels, 6, 6, seed=66)
+    dist = rv.DiagonalGaussianDistribution(moments)
+    dist_sample = dist.mean + dist.std * noise  # == DiagonalGaussianDistribution.sample() with this noise drawn
+    torch.save({"cfg": cfg.to_dict(), "seed": 63, "checksum": checksum(enc), "names": sorted(k for k, _ in enc.named_parameters()),
+                "x": x, "out": h, "moments": moments, "noise": noise, "sample": dist_sample, "mode": dist.mode()},
+               os.path.join(HERE, "vae_encoder.pt"))
+    print("vae_encoder.pt", tuple(h.shape), float(h.abs().mean()))
 
 
 if __name__ == "__main__":

@@ -233,6 +233,31 @@ def test_im2col_s2_matches_strided_conv():
     assert rel_l2(out, ref) < 3e-3
 
 
+@pytest.mark.parametrize("tc", [True, False])
+def test_stride2_conv_padded_bottom_right_only(tc):
+    """the VAE encoder's Downsample2D(padding=0): F.pad (0, 1, 0, 1) then a pad-0 stride-2 conv; tcgen05 path via the
+    im2col gather, fp32 check mode inside the SIMT conv"""
+    n, H, W, C, Cout = 2, 16, 24, 64, 128
+    dt = torch.bfloat16 if tc else torch.float32
+    x = rnd(n, H, W, C, seed=1)
+    w = rnd(Cout, 9 * C, seed=2, scale=0.04, dtype=dt)
+    M = n * (H // 2) * (W // 2)
+    out = torch.full((M, Cout), float("nan"), device=DEV)
+    if tc:
+        cols = torch.empty(M, 9 * C, device=DEV, dtype=dt)
+        ops.im2col3x3_s2(x, cols, n_img=n, H=H, W=W, C=C, asym=True)
+        ops.gemm(cols, w, out, M=M, N=Cout, K=9 * C, tc=True)
+    else:
+        ops.gemm(x.reshape(-1, C), w, out, M=M, N=Cout, K=9 * C, conv=dict(n_img=n, H=H, W=W, Cin=C, stride=2, asym=1), tc=False)
+    torch.cuda.synchronize()
+    xx = x.to(dt).float().permute(0, 3, 1, 2)
+    w4 = w.float().reshape(Cout, 3, 3, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(xx, (0, 1, 0, 1)), w4, stride=2).permute(0, 2, 3, 1).reshape(M, Cout)
+    assert rel_l2(out, ref) < (3e-3 if tc else 2e-5)
+    with pytest.raises(Exception):
+        ops.im2col3x3_s2(x[:, :15].contiguous(), torch.empty(8, 9 * C, device=DEV, dtype=torch.bfloat16), n_img=n, H=15, W=W, C=C, asym=True)
+
+
 def test_conv3x3_direct_layouts():
     n, H, W, Cin, Cout = 2, 16, 8, 4, 64
     x = rnd(n, Cin, H, W, seed=1)

@@ -174,3 +174,21 @@ def test_vae_decoder_vs_reference_run():
         full = ov.AutoencoderKLDecoder(ov.sdxl_vae())
     # decoder half of the SDXL VAE (83.65 M parameters in total, 49,490,199 of them in post_quant_conv + decoder)
     assert sum(p.numel() for p in full.parameters()) == 49_490_199
+
+
+def test_vae_encoder_and_distribution_vs_reference_run():
+    """oracle Encoder vs the reference's Encoder.forward run verbatim; DiagonalGaussianDistribution sample / mode"""
+    from oracle import vae as ov
+
+    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    enc = ov.Encoder(cfg)
+    assert sorted(k for k, _ in enc.named_parameters()) == g["names"]
+    seeded_init(enc, g["seed"])
+    assert abs(checksum(enc) - g["checksum"]) < 1e-6 * g["checksum"]
+    assert rel(enc(g["x"]), g["out"]) < 1e-5
+    assert rel(ov.gaussian_sample(g["moments"], g["noise"]), g["sample"]) < 1e-6
+    assert torch.equal(ov.gaussian_sample(g["moments"]), g["mode"])
+    with torch.device("meta"):
+        full = ov.AutoencoderKL(ov.sdxl_vae())
+    assert sum(p.numel() for p in full.parameters()) == 83_653_863  # SDXL AutoencoderKL

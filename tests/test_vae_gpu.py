@@ -143,3 +143,99 @@ def test_full_size_sdxl_vae_decode_bf16_vs_fp32_check_mode():
     b = vae.decode(z2).sample
     torch.cuda.synchronize()
     assert a.shape == (1, 3, 1024, 1024) and torch.isfinite(a).all() and torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ encode
+def _full_oracle_vae(cfg, seed=81):
+    vae = ov.AutoencoderKL(cfg)
+    seeded_init(vae, seed)
+    return vae.eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_encoder_vs_reference_run_vector(precision, tol):
+    """product Encoder vs the reference's own Encoder.forward output (tests/golden/make_golden_vae.py): stride-2
+    convs padded bottom/right only, one-head mid attention on a 8x6 grid, 8-channel conv_out"""
+    from instantir_b200.vae import vae_param_shapes
+
+    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    ovae = _full_oracle_vae(cfg)
+    seeded_init(ovae.encoder, g["seed"])
+    L2 = 2 * cfg.latent_channels
+    with torch.no_grad():
+        ovae.quant_conv.weight.copy_(torch.eye(L2).reshape(L2, L2, 1, 1))
+        ovae.quant_conv.bias.zero_()
+    sd = ovae.state_dict()
+    shapes = vae_param_shapes(VaeConfig(**cfg.to_dict()))
+    assert set(shapes) == set(sd) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    vae = AutoencoderKL(VaeConfig(**cfg.to_dict()), weights.StateDictSource(sd, DEV), DEV, precision)
+    dist = vae.encode(g["x"].to(DEV)).latent_dist
+    torch.cuda.synchronize()
+    assert dist.parameters.shape == g["out"].shape
+    assert rel_l2(dist.parameters, g["out"]) < tol
+
+
+def test_gaussian_distribution_vs_reference_run_vector():
+    from instantir_b200 import ops
+    from instantir_b200.vae import DiagonalGaussianDistribution
+
+    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    m, noise = g["moments"].to(DEV), g["noise"].to(DEV).contiguous()
+    m[0, 4:, 0, 0] = 50.0   # logvar above the clamp at 20
+    m[1, 4:, 1, 1] = -80.0  # and below the clamp at -30
+    mean, logvar = m.cpu().chunk(2, dim=1)
+    ref = mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * g["noise"]
+    out = ops.gaussian_sample(m.contiguous(), noise, torch.empty_like(noise), scale=1.0)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-6
+    assert rel_l2(ops.gaussian_sample(g["moments"].to(DEV), noise, torch.empty_like(noise)), g["sample"]) < 1e-6
+    d = DiagonalGaussianDistribution(g["moments"].to(DEV))
+    assert torch.equal(d.mode().cpu(), g["mode"])
+    s = d.sample(torch.Generator().manual_seed(9), scale=0.5)
+    n9 = torch.randn(g["noise"].shape, generator=torch.Generator().manual_seed(9))
+    assert rel_l2(s, 0.5 * ov.gaussian_sample(g["moments"], n9)) < 1e-6
+
+
+@pytest.mark.parametrize("precision,min_psnr", [("fp32", 60.0), ("bf16", 38.0)])
+def test_pipeline_from_pixels_to_pixels_psnr_vs_oracle(precision, min_psnr):
+    """the whole f1 row around the loop: a 3-channel image in [-1, 1] -> vae.encode -> sample * scaling_factor ->
+    2 denoising steps (previewer off) -> vae.decode -> image, against the oracle doing the same with the same draws"""
+    oc = ocfg.tiny()
+    ounet, oagg = build_oracle(oc, seed=0)
+    vcfg = ov.tiny_vae()
+    ovae = _full_oracle_vae(vcfg)
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    gi = torch.Generator().manual_seed(77)
+    img_in = (torch.rand(1, 3, 128, 128, generator=gi) * 2 - 1) * 0.8
+    kw = dict(num_inference_steps=2, guidance_scale=7.0, preview_start=1.0)
+    g = torch.Generator().manual_seed(42)
+    lq = ov.image_to_latents(ovae, img_in, torch.randn(1, 4, 32, 32, generator=g))
+    ref_lat = opipe.restore_latents(
+        ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=lq,
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], generator=g, **kw)
+    ref_img = ov.latents_to_image(ovae, ref_lat)
+    usd, _ = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = pcfg.ModelConfig(**oc.to_dict())
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV), DEV, precision)
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, precision)
+    vae = AutoencoderKL(VaeConfig(**vcfg.to_dict()), weights.StateDictSource(ovae.state_dict(), DEV), DEV, precision)
+    lq_p = vae.encode(img_in.to(DEV)).latent_dist.sample(torch.Generator().manual_seed(42), scale=vcfg.scaling_factor)
+    assert rel_l2(lq_p, lq) < (1e-4 if precision == "fp32" else 2e-2)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler(), vae=vae)
+    img = pipe(image=img_in, prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+               pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+               ip_adapter_image_embeds=[inp["ip"]], previewer_scheduler=LCMSingleStepScheduler(),
+               generator=torch.Generator().manual_seed(42), output_type="pt", **kw).images
+    torch.cuda.synchronize()
+    p = ov.psnr(img.cpu(), ref_img)
+    assert p >= min_psnr, f"{precision}: PSNR {p:.1f} dB"
+    with pytest.raises(TypeError):
+        InstantIRPipeline(unet, agg, DDPMScheduler())(image=img_in, prompt_embeds=inp["prompt_embeds"],
+                                                      pooled_prompt_embeds=inp["pooled_prompt_embeds"],
+                                                      negative_prompt_embeds=inp["negative_prompt_embeds"],
+                                                      negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+                                                      ip_adapter_image_embeds=[inp["ip"]])

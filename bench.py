@@ -2,19 +2,24 @@
 """bench.py — InstantIR denoising-step benchmark (driver contract, hot-path tier).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg-parallel]
-                    [--workload config2|config3|config1] [--batch B]
+                    [--workload config1..config5] [--batch B] [--precision bf16|fp16]
+                    [--no-cpu] [--no-fp16] [--no-vae] [--agg-ahead] [--profiler-range]
 
 A "step" is one denoising step of the hot path over one batch of synthetic input:
 Aggregator forward + UNet forward (both CFG branches) + fused CFG/DDPM update (+ previewer UNet
-forward and LCM step for config3).  Default workload = BASELINE.json configs[1]: full SDXL UNet +
+forward and LCM step for config3/4/5).  Default workload = BASELINE.json configs[1]: full SDXL UNet +
 InstantIR aggregator, random-init weights, 1024² (latent 128²), 30-step schedule, CFG 7, previewer off.
+config3 = + previewer every step; config4 = previewer, control_guidance_end 0.6 (12 UNet-only steps);
+config5 = 2048² with previewer.
 
 metric  = 1024² restored images / s (one image = 30 steps), whole job over all ranks
 value   = device-timed, inputs resident in HBM (CUDA events, max over ranks)
 e2e     = the same metric through the public API (InstantIRPipeline.__call__) from pinned HOST
           buffers: H2D of the image's conditioning, context refresh, 30 steps, D2H of the result
 roofline= the dominant kernel class (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs of its
-          launches in one step / their CUDA-event time, vs MEASURED_PEAKS.json
+          launches in one step / their CUDA-event time (in-graph event nodes, ONE stream), vs
+          MEASURED_PEAKS.json
+vae_decode = (N = 1) device time of the SDXL VAE decode of the final latents, and e2e with it
 cpu_baseline = the CPU oracle (port of the reference path) on this box's host cores, bounded sample
 """
 from __future__ import annotations

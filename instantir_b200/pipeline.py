@@ -423,16 +423,36 @@ class InstantIRPipeline:
         loop.step = step
         if kwargs.get("prepare_only"):
             return loop
+        callback_on_step_end = kwargs.get("callback_on_step_end")
+        callback, callback_steps = kwargs.get("callback"), kwargs.get("callback_steps") or 1
         for i in range(n):
             step(i)
+            if callback_on_step_end is not None:  # :1650-1658: the callback may replace the latents
+                names = kwargs.get("callback_on_step_end_tensor_inputs", ["latents"])
+                avail = {"latents": loop.latents, "prompt_embeds": prompt_embeds, "negative_prompt_embeds": negative_prompt_embeds}
+                outputs = callback_on_step_end(self, i, ts[i], {k: avail[k] for k in names}) or {}
+                loop.latents = outputs.pop("latents", loop.latents)
+            if callback is not None and i % callback_steps == 0:  # deprecated form (:1660-1664)
+                callback(i // getattr(sched, "order", 1), ts[i], loop.latents)
         latents, preview_row = loop.latents, loop.preview_row
         if output_type != "latent":
-            # pipelines/sdxl_instantir.py:1670-1704: latents / scaling_factor -> vae.decode -> postprocess.  The stock
-            # SDXL VAE config has no latents_mean / latents_std (:1676-1689); preview rows stay latents here.
+            # pipelines/sdxl_instantir.py:1670-1725: (latents * std / scaling_factor + mean | latents / scaling_factor) ->
+            # vae.decode -> postprocess, for the result and, with save_preview_row, for every stored preview latent
             from .vae import postprocess
 
-            image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False)[0]
-            latents = postprocess(image, output_type)
+            vcfg = self.vae.config
+            mean, std = getattr(vcfg, "latents_mean", None), getattr(vcfg, "latents_std", None)
+
+            def to_image(z):
+                if mean is not None and std is not None:
+                    z = z * torch.tensor(std, **f32).view(1, -1, 1, 1) / vcfg.scaling_factor + torch.tensor(mean, **f32).view(1, -1, 1, 1)
+                else:
+                    z = z / vcfg.scaling_factor
+                return postprocess(self.vae.decode(z, return_dict=False)[0], output_type)
+
+            latents = to_image(latents)
+            if save_preview_row:
+                preview_row = [to_image(pz) for pz in preview_row]
         if not return_dict:
             return (latents, preview_row) if save_preview_row else (latents,)
         return SimpleNamespace(images=latents, preview_rows=preview_row if save_preview_row else None)

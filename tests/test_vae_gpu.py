@@ -239,3 +239,38 @@ def test_pipeline_from_pixels_to_pixels_psnr_vs_oracle(precision, min_psnr):
                                                       negative_prompt_embeds=inp["negative_prompt_embeds"],
                                                       negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
                                                       ip_adapter_image_embeds=[inp["ip"]])
+
+
+def test_preview_rows_are_decoded_and_step_callbacks_run():
+    """save_preview_row with an image output decodes every stored preview latent (pipelines/sdxl_instantir.py:1706-1725);
+    callback_on_step_end sees every step and may replace the latents (:1650-1658)."""
+    oc = ocfg.tiny()
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=8.0)
+    vcfg = ov.tiny_vae()
+    ovae = _oracle_vae(vcfg)
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = pcfg.ModelConfig(**oc.to_dict())
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=8.0 / oc.lora_rank), DEV, "fp32")
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, "fp32")
+    vae = AutoencoderKL(VaeConfig(**vcfg.to_dict()), weights.StateDictSource(ovae.state_dict(), DEV), DEV, "fp32")
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler(), vae=vae)
+    seen = []
+
+    def cb(p, i, t, kw):
+        seen.append((i, int(t), tuple(kw["latents"].shape)))
+        return {"latents": kw["latents"] * 1.0}
+
+    call = dict(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+                ip_adapter_image_embeds=[inp["ip"]], previewer_scheduler=LCMSingleStepScheduler(), num_inference_steps=2,
+                guidance_scale=7.0, preview_start=0.0, save_preview_row=True)
+    img, rows = pipe(generator=torch.Generator().manual_seed(42), output_type="pt", return_dict=False, callback_on_step_end=cb, **call)
+    lat, lrows = pipe(generator=torch.Generator().manual_seed(42), output_type="latent", return_dict=False, **call)
+    torch.cuda.synchronize()
+    assert seen == [(0, 501, (1, 4, 32, 32)), (1, 1, (1, 4, 32, 32))]
+    assert len(rows) == len(lrows) == 2 and rows[0].shape == (1, 3, 128, 128)
+    for r, lz in zip(rows, lrows):
+        assert torch.equal(r, postprocess(vae.decode(lz / vcfg.scaling_factor).sample))
+    assert torch.equal(img, postprocess(vae.decode(lat / vcfg.scaling_factor).sample))

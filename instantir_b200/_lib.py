@@ -121,6 +121,8 @@ def load(build_if_missing: bool = True, h16: int = BF16):
         if h16 in _libs:
             return _libs[h16]
         path = LIB_PATH if h16 == BF16 else LIB_PATH_FP16
+        if h16 == BF16 and os.environ.get("IIR_LIB_OVERRIDE"):  # measurement builds (tools/probe_epilogue.py)
+            path = os.environ["IIR_LIB_OVERRIDE"]
         if not os.path.exists(path):
             if not build_if_missing:
                 raise IIRError(f"{path} not found; run `python -m instantir_b200.build`")

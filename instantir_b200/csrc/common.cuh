@@ -315,6 +315,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous: keeps every CTA of the cluster (its shared memory, mbarriers, TMEM) alive until all
+// peers are done with them.  No memory ordering is requested, so no MEMBAR.ALL.GPU is paid behind the epilogue's
+// global stores (the release form above waits for them to become visible GPU-wide: ~1 us at the tail of every
+// clustered launch).
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // 2-D TMA load multicast to every CTA in `mask`: the tile lands at the same smem offset, and
 // complete_tx is signalled on the mbarrier at the same offset, in each destination CTA.
 __device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
@@ -352,7 +360,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      // default semantics (.release.cta), as cutlass::arch::ClusterBarrier::arrive(cta_id): what this arrival orders is
+      // TMEM traffic (tcgen05 fences), not global memory; a cluster-scope release compiles to MEMBAR.ALL.GPU and stalls
+      // every epilogue thread of the pair's second CTA behind its own output stores, once per tile
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");

@@ -87,6 +87,8 @@ struct alignas(64) GemmTcParams {
   long long* ln_stats_zero;       // consumer: accumulator to clear for the next producer
   const float* ln_colsum;         // consumer: sum_k W'[n, k]
   float ln_inv_k, ln_eps;
+  int probe;  // measurement builds only (-DIIR_GEMM_PROBE): 1 = skip the epilogue body, 2 = skip its global stores,
+              // 3 = TMEM loads + row-phase math only, 4 = TMEM loads only
 };
 
 struct TileCoord {
@@ -352,6 +354,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
       mbar_wait_sleep(&tfull_bar[buf], acc_phase, 100000);  // a whole main loop: sleep, do not spin (power)
       tc_fence_after();
+#ifdef IIR_GEMM_PROBE
+      if (p.probe == 1) {  // how long is the kernel without any epilogue work?
+        if (pre) cp_async_wait<0>();
+        tc_fence_before();
+        if (MMA2 && rank != 0) mbar_arrive_remote(&tempty_bar[buf], 0);
+        else mbar_arrive(&tempty_bar[buf]);
+        continue;
+      }
+#endif
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
       for (int kc = 0; kc < nchunks_w; ++kc) {
         const int cc = chunk_par * 32 + CH_STRIDE * kc;
@@ -361,6 +372,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         tmem_ld32(taddr + cc, r);
         if (PAIR) tmem_ld32(taddr + half + cc, r2);
         tmem_ld_wait();
+#ifdef IIR_GEMM_PROBE
+        if (p.probe == 4) {  // ... with only the TMEM loads?
+          if (__uint_as_float(r[lane]) == 1.2345e-33f) reinterpret_cast<float*>(p.out)[0] = 0.f;  // keep the load alive
+          continue;
+        }
+#endif
         float v[32];
         const int pn = c.n0 + cc;  // packed column of r[0]
         const int on = nout0 + cc;  // output column of v[0]
@@ -435,6 +452,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
           }
         }
+#ifdef IIR_GEMM_PROBE
+        if (p.probe == 3) {  // ... with the TMEM loads and the row-phase math, but no staging / stores?
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += v[j];
+          if (acc == 1.2345e-33f) reinterpret_cast<float*>(p.out)[0] = acc;
+          continue;
+        }
+#endif
         // ---- transpose through the swizzled staging tile: row `lane`, 16-byte unit (c4 ^ (lane & 7))
         if (pre) {
           // groups still allowed in flight: the chunks after this one that were already requested
@@ -475,6 +501,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const int rl = i * 4 + crow;
           float4 x = *reinterpret_cast<const float4*>(slot + rl * 128 + ((cc4 ^ (rl & 7)) << 4));
           const long long m = mrow[i];
+#ifdef IIR_GEMM_PROBE
+          if (p.probe == 2) continue;  // ... and without the global stores?
+#endif
           if (m >= 0 && col_ok) {
             if (p.residual && !pre) {
               float4 q = p.res_bf16
@@ -498,14 +527,20 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         atomicAdd(acc + 1, static_cast<unsigned long long>(__float2ll_rn(ln_s2 * LN_S2_SCALE)));
       }
       tc_fence_before();
-      if (MMA2 && rank != 0) mbar_arrive_remote(&tempty_bar[buf], 0);  // the leader's MMA thread waits for both
-      else mbar_arrive(&tempty_bar[buf]);
+      // the leader's MMA thread waits for both CTAs' epilogues before it reuses this accumulator buffer.  When no later
+      // tile will reuse it nobody waits for the arrival, and the remote one is skipped: no cross-CTA traffic may still
+      // be in flight towards the leader when the (execution-only) cluster rendezvous at the end lets it exit
+      if (MMA2 && rank != 0) {
+        if (tile + NBUF * tile_step < num_tiles) mbar_arrive_remote(&tempty_bar[buf], 0);
+      } else {
+        mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / arrive on it
+  if (CL > 1) cluster_sync_relaxed();  // no CTA exits while a peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
     if (MMA2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
@@ -638,6 +673,12 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;
   p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act;
+#ifdef IIR_GEMM_PROBE
+  {
+    const char* e = getenv("IIR_GEMM_PROBE_MODE");  // read per call: the probe tool switches it between graphs
+    p.probe = e ? atoi(e) : 0;
+  }
+#endif
   if (a->ln_stats_out) {
     IIR_REQUIRE(a->pair == IIR_PAIR_NONE && (!a->residual || a->res_dtype == IIR_F32) && !a->conv,
                 "iir_gemm_tc: ln_stats_out needs a plain linear epilogue with no or an fp32 residual");

@@ -87,6 +87,7 @@ struct alignas(64) GemmTcParams {
   long long* ln_stats_zero;       // consumer: accumulator to clear for the next producer
   const float* ln_colsum;         // consumer: sum_k W'[n, k]
   float ln_inv_k, ln_eps;
+  int direct;  // row-per-thread stores straight from registers (no staging transpose)
   int probe;  // measurement builds only (-DIIR_GEMM_PROBE): 1 = skip the epilogue body, 2 = skip its global stores,
               // 3 = TMEM loads + row-phase math only, 4 = TMEM loads only
 };
@@ -364,17 +365,30 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       }
 #endif
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * ACC_STRIDE;
+      // Plain epilogues: the TMEM read of chunk k+1 is issued as soon as chunk k has left the registers for the staging
+      // tile, so it runs under chunk k's coalesced store phase instead of in front of chunk k+1's math (r is dead by
+      // then).  Paired epilogues hold two register tiles per chunk and would spill: they read at the top of the loop.
+      constexpr bool EARLY_LD = PAIR == 0;
+      uint32_t r[32];
+      uint32_t r2[32];
+      auto issue_ld = [&](int k) {
+        const int c0 = chunk_par * 32 + CH_STRIDE * k;
+        tmem_ld32(taddr + c0, r);
+        if (PAIR) tmem_ld32(taddr + half + c0, r2);
+      };
+      if (EARLY_LD && nchunks_w > 0) issue_ld(0);
       for (int kc = 0; kc < nchunks_w; ++kc) {
         const int cc = chunk_par * 32 + CH_STRIDE * kc;
         uint8_t* slot = stg + (kc % R) * EPI_STAGE_BYTES;
-        uint32_t r[32];
-        uint32_t r2[32];
-        tmem_ld32(taddr + cc, r);
-        if (PAIR) tmem_ld32(taddr + half + cc, r2);
+        if (!EARLY_LD) issue_ld(kc);
         tmem_ld_wait();
 #ifdef IIR_GEMM_PROBE
         if (p.probe == 4) {  // ... with only the TMEM loads?
-          if (__uint_as_float(r[lane]) == 1.2345e-33f) reinterpret_cast<float*>(p.out)[0] = 0.f;  // keep the load alive
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += __uint_as_float(r[j]);
+          if (acc == 1.2345e-33f) reinterpret_cast<float*>(p.out)[0] = 0.f;  // keep the load alive
+          if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
           continue;
         }
 #endif
@@ -458,9 +472,79 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc += v[j];
           if (acc == 1.2345e-33f) reinterpret_cast<float*>(p.out)[0] = acc;
+          if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
           continue;
         }
 #endif
+        // ---- DIRECT stores (16-bit outputs): every thread writes its own row's 32 consecutive outputs straight from
+        // registers (64 B: 4 stores of 16 B).  Measured against the transposed, 4-rows-per-instruction path below
+        // (tools/probe_epilogue.py): 12.7 -> 10.4 us at 2048x1280x1280, 41.9 -> 33.0 us at 4096x3840x1280 — the tile's
+        // trip through shared memory (write + syncwarp + read) costs more than the half-used store sectors.  An fp32
+        // residual still arrives through the cp.async staging ring (reading it row-per-thread from global memory is
+        // latency-bound) and is added in registers.  (The fp32 branch below is kept for IIR_GEMM_DIRECT=2 experiments.)
+        if (p.direct) {
+          if (pre) {
+            const int issued = kc + R < nchunks_w ? kc + R : nchunks_w;
+            const int pending = issued - (kc + 1);
+            if (pending <= 0) cp_async_wait<0>();
+            else if (pending == 1) cp_async_wait<1>();
+            else if (pending == 2) cp_async_wait<2>();
+            else cp_async_wait<3>();
+            __syncwarp();
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 q = *reinterpret_cast<const float4*>(slot + lane * 128 + ((c4 ^ (lane & 7)) << 4));
+              v[4 * c4] += q.x; v[4 * c4 + 1] += q.y; v[4 * c4 + 2] += q.z; v[4 * c4 + 3] += q.w;
+            }
+          }
+          if (valid) {
+            const int lim = min(ncols - cc, n_out_total - on);  // valid columns of this chunk (a multiple of 8)
+            if (p.ln_stats_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < lim) {
+                  ln_s1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                  ln_s2 += (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
+                }
+              }
+            }
+            if (p.out_bf16) {
+              h16* orow = reinterpret_cast<h16*>(p.out) + m_own * p.ld_out + on;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < lim) {
+                  uint4 u;
+                  u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+                  u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(orow + j) = u;
+                }
+              }
+            } else {
+              float* orow = reinterpret_cast<float*>(p.out) + m_own * p.ld_out + on;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (j < lim) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.ln_out16) {
+              h16* crow16 = reinterpret_cast<h16*>(p.ln_out16) + m_own * p.ld_ln16 + on;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < lim) {
+                  uint4 u;
+                  u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+                  u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(crow16 + j) = u;
+                }
+              }
+            }
+          }
+          if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
+          if (pre) {
+            __syncwarp();  // every lane has read its row of the slot before the next prefetch overwrites it
+            if (kc + R < nchunks_w) prefetch(kc + R);
+          }
+          continue;
+        }
         // ---- transpose through the swizzled staging tile: row `lane`, 16-byte unit (c4 ^ (lane & 7))
         if (pre) {
           // groups still allowed in flight: the chunks after this one that were already requested
@@ -494,6 +578,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           }
         }
         __syncwarp();
+        if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
         const int ocol = on + cc4 * 4;
         const bool col_ok = (cc + cc4 * 4 < ncols) && (ocol < n_out_total);
 #pragma unroll
@@ -673,6 +758,19 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.aux = a->aux; p.aux_bf16 = a->aux_dtype == IIR_H16; p.ld_aux = a->ld_aux;
   p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act;
+  {
+    // a residual that is NOT prefetched through the staging ring (16-bit residual) keeps the transposed path: its
+    // loads would be row-per-thread from global memory
+    static int direct_env = -1;
+    if (direct_env < 0) {
+      const char* e = getenv("IIR_GEMM_DIRECT");
+      direct_env = e ? atoi(e) : 1;
+    }
+    // ... and fp32 outputs keep it too: measured, 8 x 16 B row-per-thread stores per 128 B line (+ the 16-bit copy of a
+    // LayerNorm producer) are slower than the transposed stores (2048x1280x1280 + residual: 12.4 -> 13.6 us, with ln_out
+    // 12.8 -> 16.4 us), while 16-bit outputs gain 10-20 %
+    p.direct = direct_env && (a->out_dtype == IIR_H16 || direct_env == 2) && !(a->residual && a->res_dtype != IIR_F32);
+  }
 #ifdef IIR_GEMM_PROBE
   {
     const char* e = getenv("IIR_GEMM_PROBE_MODE");  // read per call: the probe tool switches it between graphs

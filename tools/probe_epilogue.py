@@ -22,7 +22,7 @@ class St:
         self.cur = 0
 
 
-for M, N, K in ((2048, 1280, 1280), (4096, 1280, 1280), (2048, 1280, 5120), (2048, 3840, 1280), (8192, 640, 640)):
+for M, N, K in ((2048, 1280, 1280), (4096, 1280, 1280), (2048, 3840, 1280), (4096, 3840, 1280), (8192, 640, 640), (8192, 1920, 640)):
     a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     ws = [torch.randn(N, K, device=dev, dtype=torch.bfloat16) * K ** -0.5 for _ in range(R)]
     h = torch.randn(M, N, device=dev)

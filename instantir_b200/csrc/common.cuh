@@ -151,6 +151,13 @@ __device__ __forceinline__ void st4(h16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane per instruction; p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {  // packs two h16 (name kept)
   h162 v = ff_to_h162(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -88,6 +88,7 @@ struct alignas(64) GemmTcParams {
   const float* ln_colsum;         // consumer: sum_k W'[n, k]
   float ln_inv_k, ln_eps;
   int direct;  // row-per-thread stores straight from registers (no staging transpose)
+  int wide_out, wide_ln16;  // rows of out / ln_out16 start on 32-byte boundaries: 256-bit stores
   int probe;  // measurement builds only (-DIIR_GEMM_PROBE): 1 = skip the epilogue body, 2 = skip its global stores,
               // 3 = TMEM loads + row-phase math only, 4 = TMEM loads only
 };
@@ -476,12 +477,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           continue;
         }
 #endif
-        // ---- DIRECT stores (16-bit outputs): every thread writes its own row's 32 consecutive outputs straight from
-        // registers (64 B: 4 stores of 16 B).  Measured against the transposed, 4-rows-per-instruction path below
-        // (tools/probe_epilogue.py): 12.7 -> 10.4 us at 2048x1280x1280, 41.9 -> 33.0 us at 4096x3840x1280 — the tile's
-        // trip through shared memory (write + syncwarp + read) costs more than the half-used store sectors.  An fp32
-        // residual still arrives through the cp.async staging ring (reading it row-per-thread from global memory is
-        // latency-bound) and is added in registers.  (The fp32 branch below is kept for IIR_GEMM_DIRECT=2 experiments.)
+        // ---- DIRECT stores (default): every thread writes its own row's 32 consecutive outputs straight from registers
+        // with 256-bit stores (one full 32-byte sector per lane per instruction: 2 for 16-bit, 4 for fp32 outputs).
+        // Measured against the transposed, 4-rows-per-instruction path below (tools/probe_epilogue.py, bench_lnfold.py):
+        // QKV 2048x3840x1280 21.1 -> 17.3 us, GEGLU 2048x10240x1280 42.8 -> 39.5 us, 8192x5120x640 64.2 -> 51.9 us — the
+        // tile's trip through shared memory (write + syncwarp + read) was the largest part of the exposed epilogue.  An
+        // fp32 residual still arrives through the cp.async staging ring (reading it row-per-thread from global memory is
+        // latency-bound) and is added in registers.
         if (p.direct) {
           if (pre) {
             const int issued = kc + R < nchunks_w ? kc + R : nchunks_w;
@@ -508,35 +510,45 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 }
               }
             }
-            if (p.out_bf16) {
-              h16* orow = reinterpret_cast<h16*>(p.out) + m_own * p.ld_out + on;
+            auto st16 = [&](h16* dst, bool wide) {  // 32 outputs as 16-bit: 2 x 32 B (or 4 x 16 B when rows are not 32 B aligned)
+              if (wide) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < lim) {
-                  uint4 u;
-                  u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-                  u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
-                  *reinterpret_cast<uint4*>(orow + j) = u;
-                }
+                for (int j = 0; j < 32; j += 16)
+                  if (j + 8 < lim)
+                    st_global_256(dst + j, pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                  pack_bf16(v[j + 6], v[j + 7]), pack_bf16(v[j + 8], v[j + 9]), pack_bf16(v[j + 10], v[j + 11]),
+                                  pack_bf16(v[j + 12], v[j + 13]), pack_bf16(v[j + 14], v[j + 15]));
+                  else if (j < lim)
+                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                                    pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                  if (j < lim)
+                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                                    pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
               }
+            };
+            if (p.out_bf16) {
+              st16(reinterpret_cast<h16*>(p.out) + m_own * p.ld_out + on, p.wide_out);
             } else {
               float* orow = reinterpret_cast<float*>(p.out) + m_own * p.ld_out + on;
+              if (p.wide_out) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (j < lim) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.ln_out16) {
-              h16* crow16 = reinterpret_cast<h16*>(p.ln_out16) + m_own * p.ld_ln16 + on;
+                for (int j = 0; j < 32; j += 8)
+                  if (j + 4 < lim)
+                    st_global_256(orow + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                                  __float_as_uint(v[j + 3]), __float_as_uint(v[j + 4]), __float_as_uint(v[j + 5]),
+                                  __float_as_uint(v[j + 6]), __float_as_uint(v[j + 7]));
+                  else if (j < lim)
+                    *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < lim) {
-                  uint4 u;
-                  u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-                  u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
-                  *reinterpret_cast<uint4*>(crow16 + j) = u;
-                }
+                for (int j = 0; j < 32; j += 4)
+                  if (j < lim) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               }
             }
+            if (p.ln_out16) st16(reinterpret_cast<h16*>(p.ln_out16) + m_own * p.ld_ln16 + on, p.wide_ln16);
           }
           if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
           if (pre) {
@@ -759,17 +771,19 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   p.out = a->out; p.out_bf16 = a->out_dtype == IIR_H16; p.ld_out = a->ld_out;
   p.act = a->act;
   {
-    // a residual that is NOT prefetched through the staging ring (16-bit residual) keeps the transposed path: its
-    // loads would be row-per-thread from global memory
+    // a residual that is NOT prefetched through the staging ring (16-bit residual) keeps the transposed path: its loads
+    // would be row-per-thread from global memory.  IIR_GEMM_DIRECT: 0 = transposed stores everywhere, 1 = direct for
+    // 16-bit outputs only, 2 (default) = direct for fp32 outputs too (with 256-bit stores: 2048x1280x1280 + residual
+    // 12.8 -> 11.7 us; with the 16-bit LayerNorm copy on top it is a wash, 13.1 vs 13.2 us)
     static int direct_env = -1;
     if (direct_env < 0) {
       const char* e = getenv("IIR_GEMM_DIRECT");
-      direct_env = e ? atoi(e) : 1;
+      direct_env = e ? atoi(e) : 2;
     }
-    // ... and fp32 outputs keep it too: measured, 8 x 16 B row-per-thread stores per 128 B line (+ the 16-bit copy of a
-    // LayerNorm producer) are slower than the transposed stores (2048x1280x1280 + residual: 12.4 -> 13.6 us, with ln_out
-    // 12.8 -> 16.4 us), while 16-bit outputs gain 10-20 %
     p.direct = direct_env && (a->out_dtype == IIR_H16 || direct_env == 2) && !(a->residual && a->res_dtype != IIR_F32);
+    const long long esz = a->out_dtype == IIR_H16 ? 2 : 4;
+    p.wide_out = (reinterpret_cast<uintptr_t>(a->out) % 32 == 0) && (a->ld_out * esz) % 32 == 0;
+    p.wide_ln16 = a->ln_out16 && (reinterpret_cast<uintptr_t>(a->ln_out16) % 32 == 0) && (a->ld_ln_out16 * 2) % 32 == 0;
   }
 #ifdef IIR_GEMM_PROBE
   {

@@ -41,6 +41,7 @@ struct alignas(64) AttnTcParams {
   int out_off;
   int B, heads, n_q;
   float scale_log2;  // softmax_scale * log2(e)
+  int wide_out;      // output rows start on 32-byte boundaries (256-bit stores in the attn_ts epilogue)
 };
 
 constexpr int ATT_TMEM_COLS = 256;  // S (128) + 2 x O (64): two CTAs share the SM's 512 columns
@@ -633,14 +634,28 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       tmem_ld32(tmem_O + trow + half * 32, r);
       tmem_ld_wait();
       if (qi < p.n_q) {
+        if (p.wide_out) {  // rows start on 32-byte boundaries: 256-bit stores, one full sector per lane per instruction
 #pragma unroll
-        for (int d = 0; d < 32; d += 8) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[d]) * w, __uint_as_float(r[d + 1]) * w);
-          u.y = pack_bf16(__uint_as_float(r[d + 2]) * w, __uint_as_float(r[d + 3]) * w);
-          u.z = pack_bf16(__uint_as_float(r[d + 4]) * w, __uint_as_float(r[d + 5]) * w);
-          u.w = pack_bf16(__uint_as_float(r[d + 6]) * w, __uint_as_float(r[d + 7]) * w);
-          *reinterpret_cast<uint4*>(optr + half * 32 + d) = u;
+          for (int d = 0; d < 32; d += 16)
+            st_global_256(optr + half * 32 + d,
+                          pack_bf16(__uint_as_float(r[d]) * w, __uint_as_float(r[d + 1]) * w),
+                          pack_bf16(__uint_as_float(r[d + 2]) * w, __uint_as_float(r[d + 3]) * w),
+                          pack_bf16(__uint_as_float(r[d + 4]) * w, __uint_as_float(r[d + 5]) * w),
+                          pack_bf16(__uint_as_float(r[d + 6]) * w, __uint_as_float(r[d + 7]) * w),
+                          pack_bf16(__uint_as_float(r[d + 8]) * w, __uint_as_float(r[d + 9]) * w),
+                          pack_bf16(__uint_as_float(r[d + 10]) * w, __uint_as_float(r[d + 11]) * w),
+                          pack_bf16(__uint_as_float(r[d + 12]) * w, __uint_as_float(r[d + 13]) * w),
+                          pack_bf16(__uint_as_float(r[d + 14]) * w, __uint_as_float(r[d + 15]) * w));
+        } else {
+#pragma unroll
+          for (int d = 0; d < 32; d += 8) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r[d]) * w, __uint_as_float(r[d + 1]) * w);
+            u.y = pack_bf16(__uint_as_float(r[d + 2]) * w, __uint_as_float(r[d + 3]) * w);
+            u.z = pack_bf16(__uint_as_float(r[d + 4]) * w, __uint_as_float(r[d + 5]) * w);
+            u.w = pack_bf16(__uint_as_float(r[d + 6]) * w, __uint_as_float(r[d + 7]) * w);
+            *reinterpret_cast<uint4*>(optr + half * 32 + d) = u;
+          }
         }
       }
     }
@@ -706,6 +721,7 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   p.out_off = a->out_off;
   p.B = a->B; p.heads = a->heads; p.n_q = a->n_q;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+  p.wide_out = (reinterpret_cast<uintptr_t>(a->out) % 32 == 0) && (a->ldo * 2) % 32 == 0 && (a->out_off * 2) % 32 == 0;
 
   const size_t smem = 7 * TILE_BYTES + 256;
   dim3 grid((a->n_q + 127) / 128, a->heads, a->B);

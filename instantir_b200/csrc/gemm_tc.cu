@@ -842,7 +842,10 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     while (slots > 1 && (SMEM_BUDGET - 1024 - 256 - VEC_BYTES - EW * slots * EPI_STAGE_BYTES) / stage_bytes < want) --slots;
   }
   p.epi_slots = slots;
-  const int epi_bytes = EW * slots * EPI_STAGE_BYTES;
+  // the direct-store epilogue touches the staging tiles only to receive a prefetched fp32 residual: without one their
+  // 32 KB go to the main-loop pipeline (one more stage for a 256-wide pair tile)
+  const bool need_staging = !p.direct || (a->residual && a->res_dtype == IIR_F32);
+  const int epi_bytes = need_staging ? EW * slots * EPI_STAGE_BYTES : 0;
   int stages = (SMEM_BUDGET - 1024 - 256 - VEC_BYTES - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1) stages = p.num_kb + 1 < 2 ? 2 : p.num_kb + 1;

@@ -385,7 +385,7 @@ def run_ours(args):
                 roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches in
-                        # profiles/ncu_gemm_tc_full_r01b.txt (FF1 32.0 / out-proj 19.1 / FF2 44.7 / conv 17.9 MB):
+                        # profiles/ncu_gemm_tc_full_r01d.txt (FF1 31.6 / out-proj 19.1 / FF2 44.6 / conv 17.9 MB read, < 0.4 MB written):
                         # = weights + activations once, no re-reads (outputs still sit in L2 when the kernel ends)
                         "traffic": 28.4e6,
                         "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",

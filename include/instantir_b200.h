@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 6
+#define IIR_ABI_VERSION 7
 
 typedef enum {
   IIR_OK = 0,
@@ -231,6 +231,11 @@ int iir_lcm_step(const void* eps, int eps_dtype, const float* x, float* out, int
 int iir_cfg_ddpm_step(const void* eps_uncond, const void* eps_cond, int eps_dtype, const float* x,
                       const float* noise, float* prev, float* pred_x0, int64_t n, float guidance,
                       float alpha_prod_t, float c_x0, float c_xt, float sigma, void* stream);
+/* CFG combine followed by rescale_noise_cfg (pipelines/sdxl_instantir.py:181-192, 1619-1625; guidance_rescale > 0):
+ *   cfg = eps_u + g (eps_c - eps_u);  out = cfg * (rescale * std(eps_c) / std(cfg) + 1 - rescale)
+ * with torch.std (unbiased) over each sample of n_per elements; eps fp32 [n_samples, n_per].                      */
+int iir_cfg_rescale(const float* eps_uncond, const float* eps_cond, float* out, int64_t n_samples, int64_t n_per,
+                    float guidance, float rescale, void* stream);
 /* add_noise (lcm_single_step_scheduler.py:492-513): out = sqrt(abar)*x0 + sqrt(1-abar)*noise */
 int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n, float alpha_prod_t,
                   void* stream);

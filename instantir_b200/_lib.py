@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
@@ -26,7 +26,7 @@ SYMBOLS = [
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add",
     "iir_timestep_embedding", "iir_linear_small",
-    "iir_lcm_step", "iir_cfg_ddpm_step", "iir_add_noise", "iir_gaussian_sample",
+    "iir_lcm_step", "iir_cfg_ddpm_step", "iir_cfg_rescale", "iir_add_noise", "iir_gaussian_sample",
 ]
 
 
@@ -104,6 +104,7 @@ def _declare(lib):
     lib.iir_add.argtypes = [vp, i, vp, i, vp, i, i64, vp]
     lib.iir_timestep_embedding.argtypes = [vp, i, i, vp, i, vp]
     lib.iir_linear_small.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, vp]
+    lib.iir_cfg_rescale.argtypes = [vp, vp, vp, i64, i64, f, f, vp]
     lib.iir_gaussian_sample.argtypes = [vp, vp, vp, i64, i64, f, vp]
     lib.iir_lcm_step.argtypes = [vp, i, vp, vp, i64, f, f, f, vp]
     lib.iir_cfg_ddpm_step.argtypes = [vp, vp, i, vp, vp, vp, vp, i64, f, f, f, f, f, vp]

@@ -78,6 +78,41 @@ gaussian_sample_kernel(const float* __restrict__ moments, const float* __restric
   }
 }
 
+// CFG combine + rescale_noise_cfg (pipelines/sdxl_instantir.py:181-192, 1619-1625; guidance_rescale > 0): one CTA per
+// sample.  cfg = e_u + g (e_c - e_u); out = cfg * (rescale * std(e_c) / std(cfg) + 1 - rescale), std = torch.std over the
+// sample (unbiased).  Two passes over the sample (it is read from L2 the second time); sums in fp64.
+__global__ void __launch_bounds__(1024)
+cfg_rescale_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ out, long long n_per,
+                   float g, float rescale) {
+  __shared__ double red[4][32];
+  const float* u = eu + blockIdx.x * n_per;
+  const float* c = ec + blockIdx.x * n_per;
+  float* o = out + blockIdx.x * n_per;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};  // sum / sum of squares of e_c, then of cfg
+  for (long long i = threadIdx.x; i < n_per; i += 1024) {
+    const float cv = c[i], f = u[i] + g * (cv - u[i]);
+    s[0] += cv; s[1] += static_cast<double>(cv) * cv; s[2] += f; s[3] += static_cast<double>(f) * f;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    if (lane == 0) red[k][warp] = s[k];
+  }
+  __syncthreads();
+  double t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    t[k] = 0.0;
+    for (int w = 0; w < 32; ++w) t[k] += red[k][w];  // fixed order: every thread gets the same value
+  }
+  const double n = static_cast<double>(n_per);
+  const double var_t = (t[1] - t[0] * t[0] / n) / (n - 1.0), var_c = (t[3] - t[2] * t[2] / n) / (n - 1.0);
+  const float factor = rescale * static_cast<float>(sqrt(var_t > 0 ? var_t : 0.0) / sqrt(var_c)) + (1.0f - rescale);
+  for (long long i = threadIdx.x; i < n_per; i += 1024) o[i] = (u[i] + g * (c[i] - u[i])) * factor;
+}
+
 int grid_for4(long long n4) {
   long long b = (n4 + 255) / 256;
   long long cap = 8LL * sm_count();
@@ -142,4 +177,14 @@ extern "C" int iir_gaussian_sample(const float* moments, const float* noise, flo
   gaussian_sample_kernel<<<grid_for4(total), 256, 0, st>>>(moments, noise, out, total, static_cast<long long>(half), scale);
   count_launch();
   return check_launch("iir_gaussian_sample");
+}
+
+extern "C" int iir_cfg_rescale(const float* eps_uncond, const float* eps_cond, float* out, int64_t n_samples, int64_t n_per,
+                               float guidance, float rescale, void* stream) {
+  IIR_REQUIRE(eps_uncond && eps_cond && out && n_samples > 0 && n_per > 1, "iir_cfg_rescale: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cfg_rescale_kernel<<<static_cast<unsigned>(n_samples), 1024, 0, st>>>(eps_uncond, eps_cond, out, static_cast<long long>(n_per),
+                                                                         guidance, rescale);
+  count_launch();
+  return check_launch("iir_cfg_rescale");
 }

@@ -429,3 +429,14 @@ def gaussian_sample(moments: torch.Tensor, noise, out: torch.Tensor, *, scale: f
     _lib.check(lib.iir_gaussian_sample(_p(moments), _p(noise), _p(out), B, half, float(scale), _stream()),
                "iir_gaussian_sample", lib)
     return out
+
+
+def cfg_rescale(eps_uncond, eps_cond, out, *, guidance: float, rescale: float):
+    """out = rescale_noise_cfg(e_u + g (e_c - e_u), e_c, rescale) per sample; fp32 [B, ...] tensors."""
+    lib = _L()
+    for t, n in ((eps_uncond, "eps_uncond"), (eps_cond, "eps_cond"), (out, "out")):
+        _f32c(t, n)
+    B = eps_cond.shape[0]
+    _lib.check(lib.iir_cfg_rescale(_p(eps_uncond), _p(eps_cond), _p(out), B, eps_cond[0].numel(), float(guidance), float(rescale),
+                                   _stream()), "iir_cfg_rescale", lib)
+    return out

@@ -149,9 +149,9 @@ class InstantIRPipeline:
         if prompt is not None or negative_prompt is not None or ip_adapter_image is not None:
             raise NotImplementedError("text / image encoders are outside this build's scope (SURVEY §8 f1-f2): pass "
                                       "prompt_embeds, pooled_prompt_embeds, ip_adapter_image_embeds and a latent `image`")
-        if multistep_restore or adastep_restore or guidance_rescale or denoising_end or reference_latents is not None:
-            raise NotImplementedError("multistep_restore / adastep_restore / guidance_rescale / denoising_end / "
-                                      "reference_latents are experimental reference options (SURVEY §8 f4)")
+        if multistep_restore or adastep_restore or denoising_end or reference_latents is not None:
+            raise NotImplementedError("multistep_restore / adastep_restore / denoising_end / reference_latents are "
+                                      "experimental reference options (SURVEY §8 f4)")
         if output_type != "latent":
             if self.vae is None:
                 raise ValueError("output_type != 'latent' needs a VAE: InstantIRPipeline(unet, aggregator, scheduler, vae=AutoencoderKL(...))")
@@ -410,8 +410,17 @@ class InstantIRPipeline:
                 noise_pred = g_unet_res[loop.res_src]()
             if cfg_parallel is not None:
                 noise_pred = cfg_parallel.gather_branches(noise_pred)  # [2B,4,h,w] = [uncond; cond]
+            g_step_arg = guidance_scale if do_cfg else None
+            if do_cfg and guidance_rescale > 0.0:
+                # rescale_noise_cfg (:181-192, :1623-1625): needs the per-sample std of the guided and of the text
+                # prediction, so the combine leaves the fused CFG+DDPM kernel for a one-CTA-per-sample kernel
+                nb_ = noise_pred.shape[0] // 2
+                eps32 = noise_pred.float().contiguous()
+                noise_pred = ops.cfg_rescale(eps32[:nb_], eps32[nb_:], torch.empty_like(eps32[:nb_]), guidance=guidance_scale,
+                                             rescale=guidance_rescale)
+                g_step_arg = None
             out = sched.step(noise_pred, t_int, lat, generator=generator, return_dict=True,
-                             guidance=guidance_scale if do_cfg else None,
+                             guidance=g_step_arg,
                              noise=draw(lat.shape) if t_int > 0 else None)
             loop.latents = out.prev_sample
             if record is not None:

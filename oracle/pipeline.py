@@ -27,7 +27,7 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                     ip_image_embeds, add_time_ids, num_inference_steps=30, guidance_scale=7.0,
                     preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                     controlnet_conditioning_scale=1.0, generator=None, init_latents_with_lq=True,
-                    timesteps=None, record: Optional[dict] = None):
+                    timesteps=None, record: Optional[dict] = None, guidance_rescale: float = 0.0):
     """Returns the final latents [B,4,h,w]; `record` (if given) collects per-step tensors.
 
     image: LQ latent [B,4,h,w] (the reference accepts 4-channel tensors as latents, :1370-1382).
@@ -89,6 +89,10 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
         if do_cfg:
             e_u, e_c = noise_pred.chunk(2)
             noise_pred = e_u + guidance_scale * (e_c - e_u)
+            if guidance_rescale > 0.0:  # rescale_noise_cfg, pipelines/sdxl_instantir.py:181-192, 1623-1625
+                dims = list(range(1, e_c.ndim))
+                std_text, std_cfg = e_c.std(dim=dims, keepdim=True), noise_pred.std(dim=dims, keepdim=True)
+                noise_pred = guidance_rescale * noise_pred * (std_text / std_cfg) + (1 - guidance_rescale) * noise_pred
         out = scheduler.step(noise_pred, t, latents, generator=generator, return_dict=True)
         latents = out.prev_sample
         if record is not None:

@@ -581,3 +581,17 @@ def test_softmax_rows(odt, rows, n):
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out, ref) < (2e-6 if odt == torch.float32 else 4e-3)
     assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=1e-5 if odt == torch.float32 else 2e-2)
+
+
+def test_cfg_rescale_matches_rescale_noise_cfg():
+    """iir_cfg_rescale vs the reference's rescale_noise_cfg arithmetic (pipelines/sdxl_instantir.py:181-192) in fp64"""
+    B, shape, g, phi = 3, (4, 32, 48), 7.0, 0.7
+    eu, ec = rnd(B, *shape, seed=1), rnd(B, *shape, seed=2) * 1.3 + 0.2
+    out = torch.full((B, *shape), float("nan"), device=DEV)
+    ops.cfg_rescale(eu, ec, out, guidance=g, rescale=phi)
+    torch.cuda.synchronize()
+    u, c = eu.double(), ec.double()
+    cfg = u + g * (c - u)
+    dims = [1, 2, 3]
+    ref = phi * cfg * (c.std(dim=dims, keepdim=True) / cfg.std(dim=dims, keepdim=True)) + (1 - phi) * cfg
+    assert rel_l2(out, ref) < 1e-6

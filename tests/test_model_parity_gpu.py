@@ -257,6 +257,40 @@ def test_aggregator_ahead_mixed_with_preview_steps_bf16():
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
+def test_guidance_rescale_fp32():
+    """guidance_rescale = 0.7 (rescale_noise_cfg, pipelines/sdxl_instantir.py:181-192): per-sample std rescaling of the
+    guided prediction through iir_cfg_rescale, against the oracle's restatement; batch 2 so the two samples get
+    different factors."""
+    oc = ocfg.tiny()
+    ounet, oagg = build_oracle(oc, seed=0, lora_alpha=8.0)
+    inp = make_inputs(oc, B=2, h=32, w=32)
+    kw = dict(num_inference_steps=2, guidance_scale=7.0, preview_start=0.0)
+    ref = opipe.restore_latents(
+        ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], generator=torch.Generator().manual_seed(42),
+        guidance_rescale=0.7, **kw)
+    plain = opipe.restore_latents(
+        ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], generator=torch.Generator().manual_seed(42), **kw)
+    assert rel_l2(ref, plain) > 1e-2  # the option changes the result, so the check below is not vacuous
+    usd, ulora = export_state(ounet)
+    asd, _ = export_state(oagg)
+    pc = _pcfg_from(oc)
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV, lora=ulora, lora_scale=8.0 / oc.lora_rank), DEV, "fp32")
+    agg = Aggregator(pc, weights.StateDictSource(asd, DEV), DEV, "fp32")
+    out = InstantIRPipeline(unet, agg, DDPMScheduler())(
+        image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_adapter_image_embeds=[inp["ip"]], previewer_scheduler=LCMSingleStepScheduler(),
+        generator=torch.Generator().manual_seed(42), guidance_rescale=0.7, **kw).images
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-4
+
+
 def test_guidance_scale_le_1_disables_cfg_fp32():
     ref, _, out, _ = _run_pair("fp32", steps=1, guidance=1.0, graph=False)
     assert rel_l2(out, ref) < 1e-4

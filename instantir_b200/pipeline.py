@@ -4,10 +4,11 @@ the sm_100a kernels, with the reference's call surface for this path: ``guidance
 ``previewer_scheduler``, ``num_inference_steps``, ``generator``, ``timesteps``,
 ``controlnet_conditioning_scale``, ``init_latents_with_lq``, ``save_preview_row``...
 
-Scope: the per-timestep step.  The once-per-image encoders (CLIP text, DINOv2, VAE) are
-"next" rows, so this pipeline takes their OUTPUTS: ``prompt_embeds`` / ``pooled_prompt_embeds`` (and
-negatives), ``ip_adapter_image_embeds`` (DINOv2 tokens) and a 4-channel LQ latent as ``image`` (the
-reference accepts latents there too, :1370-1382) and returns latents (``output_type="latent"``).
+Scope: the per-timestep step, plus the VAE of row f1.  The once-per-image CLIP text and DINOv2
+encoders are "next" rows, so this pipeline takes their OUTPUTS: ``prompt_embeds`` / ``pooled_prompt_embeds``
+(and negatives) and ``ip_adapter_image_embeds`` (DINOv2 tokens).  ``image`` is a 4-channel LQ latent (the
+reference accepts latents there too, :1370-1382) or, when the pipeline was given ``vae=``, a 3-channel image in
+[-1, 1] that is encoded here; the result is latents (``output_type="latent"``) or decoded images ("pt" / "np").
 
 What changes versus the reference's loop (same results, fewer launches):
   * which of the three step shapes runs at step i (previewer+aggregator+UNet / aggregator+UNet /

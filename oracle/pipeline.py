@@ -21,6 +21,15 @@ def step_masks(n_steps, preview_start, preview_end, control_guidance_start, cont
     return keep, prev
 
 
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """pipelines/sdxl_instantir.py:181-192: pull the guided prediction's per-sample std back to the text branch's and
+    blend by `guidance_rescale` (torch.std = unbiased)."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text, std_cfg = noise_pred_text.std(dim=dims, keepdim=True), noise_cfg.std(dim=dims, keepdim=True)
+    noise_pred_rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * noise_pred_rescaled + (1 - guidance_rescale) * noise_cfg
+
+
 @torch.no_grad()
 def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, prompt_embeds,
                     negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
@@ -89,10 +98,8 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
         if do_cfg:
             e_u, e_c = noise_pred.chunk(2)
             noise_pred = e_u + guidance_scale * (e_c - e_u)
-            if guidance_rescale > 0.0:  # rescale_noise_cfg, pipelines/sdxl_instantir.py:181-192, 1623-1625
-                dims = list(range(1, e_c.ndim))
-                std_text, std_cfg = e_c.std(dim=dims, keepdim=True), noise_pred.std(dim=dims, keepdim=True)
-                noise_pred = guidance_rescale * noise_pred * (std_text / std_cfg) + (1 - guidance_rescale) * noise_pred
+            if guidance_rescale > 0.0:  # pipelines/sdxl_instantir.py:1623-1625
+                noise_pred = rescale_noise_cfg(noise_pred, e_c, guidance_rescale)
         out = scheduler.step(noise_pred, t, latents, generator=generator, return_dict=True)
         latents = out.prev_sample
         if record is not None:

@@ -192,3 +192,13 @@ def test_vae_encoder_and_distribution_vs_reference_run():
     with torch.device("meta"):
         full = ov.AutoencoderKL(ov.sdxl_vae())
     assert sum(p.numel() for p in full.parameters()) == 83_653_863  # SDXL AutoencoderKL
+
+
+def test_rescale_noise_cfg_vs_reference_run():
+    """oracle.pipeline.rescale_noise_cfg vs the reference's own function executed verbatim (make_golden_misc.py)"""
+    from oracle import pipeline as opipe
+
+    g = torch.load(os.path.join(G, "rescale_noise_cfg.pt"), weights_only=False)
+    cfg = g["e_u"] + g["guidance"] * (g["e_c"] - g["e_u"])
+    for phi, want in g["out"].items():
+        assert torch.equal(opipe.rescale_noise_cfg(cfg, g["e_c"], phi), want), phi

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 7
+#define IIR_ABI_VERSION 8
 
 typedef enum {
   IIR_OK = 0,
@@ -209,6 +209,9 @@ int iir_silu(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, vo
 int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, void* out, int out_dtype,
             int64_t n, void* stream);
 
+/* out = alpha * x  (Aggregator.forward's `conditioning_scale`, module/aggregator.py:963-964)       */
+int iir_scale(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, float alpha, void* stream);
+
 /* sinusoidal timestep embedding [cos|sin], flip_sin_to_cos=True, freq_shift=0
  * (module/min_sdxl.py:205-224): t [n] fp32 -> out [n, dim]                                  */
 int iir_timestep_embedding(const float* t, int n, int dim, void* out, int out_dtype, void* stream);
@@ -220,6 +223,11 @@ int iir_linear_small(const void* x, int x_dtype, const void* w, int w_dtype, con
 /* ------------------------------------------------------------------------------------------
  * Scheduler / guidance kernels (fp32 latents, NCHW [B,4,h,w] flattened)
  * ---------------------------------------------------------------------------------------- */
+/* Start of a denoising step (pipelines/sdxl_instantir.py:1503-1506,1538-1540): x_in = cat([latents] * n_rep)
+ * (latent_model_input; scale_model_input is the identity for DDPM), *t_dev = t, cond_scale_dev[0..n_cond) =
+ * cond_scale.  latents fp32 [n]; x_in fp32 [n_rep * n]; t_dev / cond_scale_dev may be NULL.                       */
+int iir_step_prologue(const float* latents, int64_t n, int n_rep, float* x_in, float t, float* t_dev,
+                      float cond_scale, float* cond_scale_dev, int n_cond, void* stream);
 /* LCM single-step preview: schedulers/lcm_single_step_scheduler.py:421-489
  *   x0 = (x - sqrt(1-abar) eps)/sqrt(abar);  out = c_out*x0 + c_skip*x                      */
 int iir_lcm_step(const void* eps, int eps_dtype, const float* x, float* out, int64_t n,

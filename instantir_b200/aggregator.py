@@ -54,8 +54,65 @@ class SFTHead:
         return FMap(out, n, H, W, C).nchw()
 
 
+class _FromUNetSource:
+    """weight source of Aggregator.from_unet (module/aggregator.py:564-576): trunk tensors come from the UNet's own
+    source, SFT-head convolutions get torch's default Conv2d initialisation (kaiming_uniform(a=sqrt 5) weights,
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) biases; seeded), the closing 1x1 convolutions are zero (zero_module, :980-983)."""
+
+    def __init__(self, cfg, unet_source, device, seed=0):
+        from .weights import aggregator_param_shapes
+
+        self.shapes, self.src, self.device, self.seed = aggregator_param_shapes(cfg), unet_source, device, seed
+
+    def has(self, key):
+        return key in self.shapes
+
+    def get(self, key):
+        if key not in self.shapes:
+            raise KeyError(f"missing weight '{key}'")
+        if key.startswith("ref_conv_in."):
+            return self.src.get("conv_in." + key.split(".", 1)[1])
+        if not key.startswith("controlnet_"):
+            return self.src.get(key)
+        shape = self.shapes[key]
+        head_out = key.startswith("controlnet_mid_block.1.") or (key.startswith("controlnet_down_blocks.") and key.split(".")[2] == "1")
+        if head_out:
+            return torch.zeros(shape, device=self.device, dtype=torch.float32)
+        import hashlib
+
+        wshape = self.shapes[key.rsplit(".", 1)[0] + ".weight"]
+        fan_in = wshape[1] * wshape[2] * wshape[3]
+        bound = fan_in ** -0.5  # kaiming_uniform(a=sqrt(5)): gain sqrt(2/6) * sqrt(3/fan_in) = 1/sqrt(fan_in); same for the bias
+        h = int.from_bytes(hashlib.sha256(f"{self.seed}:{key}".encode()).digest()[:6], "little")
+        g = torch.Generator(device="cpu").manual_seed(h)
+        return ((torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound).to(self.device)
+
+    def get_lora(self, module):
+        return None
+
+
+class _OverlaySource:
+    """load_state_dict(strict=False): keys absent from the new state dict keep their current values"""
+
+    def __init__(self, sd, base, device):
+        self.sd, self.base, self.device = sd, base, device
+
+    def has(self, key):
+        return key in self.sd or self.base.has(key)
+
+    def get(self, key):
+        if key in self.sd:
+            return self.sd[key].detach().to(device=self.device, dtype=torch.float32)
+        return self.base.get(key)
+
+    def get_lora(self, module):
+        return None
+
+
 class Aggregator(_EmbeddingMixin):
-    def __init__(self, cfg: ModelConfig, source, device="cuda", precision="bf16"):
+    weights_version = 0
+
+    def __init__(self, cfg: ModelConfig, source, device="cuda", precision="fp16"):
         self.cfg, self.source = cfg, source
         self.rt = rt = Runtime(device, precision)
         ch = cfg.block_out_channels
@@ -84,10 +141,50 @@ class Aggregator(_EmbeddingMixin):
                                   cfg.transformer_layers_per_block[-1], cross=False)
 
     @classmethod
-    def from_unet(cls, unet, **kw):
-        raise NotImplementedError(
-            "Aggregator.from_unet builds an untrained aggregator whose outputs are exactly zero "
-            "(module/aggregator.py:414-417,503-578); construct Aggregator(cfg, source) from aggregator.pt weights")
+    def from_unet(cls, unet, controlnet_conditioning_channel_order="rgb", conditioning_embedding_out_channels=None,
+                  load_weights_from_unet=True, conditioning_channels=3, seed=0, precision=None):
+        """module/aggregator.py:503-578, as the pipeline uses it (pipelines/sdxl_instantir.py:320-322: from_unet followed
+        by remove_attn2): conv_in and ref_conv_in both start from the UNet's conv_in, time / add embeddings, down
+        blocks and mid block are copies of the UNet's (minus attn2 / norm2), the SFT heads are freshly initialised
+        (torch's default Conv2d init, seeded) and every head ends in a zero 1x1 convolution — so the residuals of a
+        from_unet aggregator are exactly zero until `load_state_dict(aggregator.pt)` (infer.py:142-144)."""
+        if not load_weights_from_unet:
+            raise NotImplementedError("from_unet(load_weights_from_unet=False): random trunk weights have no use at inference")
+        src = _FromUNetSource(unet.cfg, unet.source, unet.rt.device, seed)
+        agg = cls(unet.cfg, src, unet.rt.device, precision or unet.rt.precision)
+        agg.config.controlnet_conditioning_channel_order = controlnet_conditioning_channel_order
+        return agg
+
+    def state_dict_keys(self):
+        """key -> shape of the state dict this module loads (module/aggregator.py:414-471 after remove_attn2)"""
+        from .weights import aggregator_param_shapes
+
+        return aggregator_param_shapes(self.cfg)
+
+    def load_state_dict(self, state_dict, strict=True):
+        """infer.py:142-144 / gradio_demo/app.py:81: (re)pack every layer from `state_dict` (aggregator.pt key layout,
+        SURVEY Appendix D).  Returns (missing_keys, unexpected_keys) like torch; strict=True raises on either.
+        Pipelines notice the new weights through `weights_version` and re-capture their CUDA graphs."""
+        from types import SimpleNamespace as NS
+
+        from .weights import StateDictSource
+
+        want = self.state_dict_keys()
+        missing = [k for k in want if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in want]
+        bad = [k for k in want if k in state_dict and tuple(state_dict[k].shape) != tuple(want[k])]
+        if bad:
+            raise RuntimeError("size mismatch for " + ", ".join(f"{k}: {tuple(state_dict[k].shape)} vs {tuple(want[k])}" for k in bad[:8]))
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for Aggregator: missing {missing[:8]}{'...' if len(missing) > 8 else ''}, "
+                               f"unexpected {unexpected[:8]}{'...' if len(unexpected) > 8 else ''}")
+        src = StateDictSource(state_dict, self.rt.device) if not missing else _OverlaySource(state_dict, self.source, self.rt.device)
+        version = self.weights_version + 1
+        order = self.config.controlnet_conditioning_channel_order
+        self.__init__(self.cfg, src, self.rt.device, self.rt.precision)
+        self.weights_version = version
+        self.config.controlnet_conditioning_channel_order = order
+        return NS(missing_keys=missing, unexpected_keys=unexpected)
 
     def __call__(self, *a, **kw):
         return self.forward(*a, **kw)
@@ -105,8 +202,6 @@ class Aggregator(_EmbeddingMixin):
             raise ValueError(f"unknown `controlnet_conditioning_channel_order`: {self.config.controlnet_conditioning_channel_order}")
         if cat_dim not in (-2, 2):
             raise ValueError(f"Aggregator shall concat along spatial dimension H (cat_dim=-2), but is asked to concat dim: {cat_dim}.")
-        if conditioning_scale != 1.0:
-            raise NotImplementedError("conditioning_scale != 1 (the pipeline never passes it, pipelines/sdxl_instantir.py:1596)")
         rt, cfg = self.rt, self.cfg
         rt.new_forward()
         n, _, H, W = sample.shape
@@ -140,6 +235,14 @@ class Aggregator(_EmbeddingMixin):
         for i in range(done, len(skips)):
             down[i] = self.controlnet_down_blocks[i](skips[i], ob_down[i])
         mid = self.controlnet_mid_block(x, ob_mid)
+        if conditioning_scale != 1.0:
+            # module/aggregator.py:963-964: every residual times conditioning_scale (the pipeline itself always passes
+            # 1.0 and scales by cond_scale inside the UNet's fused concat, pipelines/sdxl_instantir.py:1596,1602-1603)
+            if head_stream is not None:
+                torch.cuda.current_stream().wait_stream(head_stream)
+            for r in down + [mid]:
+                flat = r.permute(0, 2, 3, 1)  # NHWC memory behind the NCHW view
+                ops.scale(flat, flat, float(conditioning_scale))
         if not return_dict:
             return (down, mid)
         return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)

@@ -33,14 +33,21 @@ int check_launch(const char* what) {
 }
 
 int sm_count() {
-  static int n = 0;
+  // per device: a process may drive several GPUs (one per rank is the norm, but nothing forbids more)
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;  // B200
+  }
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  int n = cache[slot].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = 148;  // B200
+      n = 148;
     }
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
 }

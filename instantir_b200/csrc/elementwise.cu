@@ -117,6 +117,12 @@ add_kernel(const void* a, int a_bf, const void* b, int b_bf, void* out, int out_
     st1_any(out, out_bf, i, ld1_any(a, a_bf, i) + ld1_any(b, b_bf, i));
 }
 
+__global__ void __launch_bounds__(256)
+scale_kernel(const void* x, int x_bf, void* out, int out_bf, long long n, float alpha) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+    st1_any(out, out_bf, i, alpha * ld1_any(x, x_bf, i));
+}
+
 // [cos | sin] of t * exp(-ln(10000) * k / half), fp32 like the reference (min_sdxl.py:205-224)
 __global__ void timestep_embedding_kernel(const float* t, int n, int dim, void* out, int out_bf) {
   const int half = dim >> 1;
@@ -214,6 +220,15 @@ extern "C" int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, v
                                           out_dtype == IIR_H16, n);
   count_launch();
   return check_launch("iir_add");
+}
+
+extern "C" int iir_scale(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, float alpha, void* stream) {
+  IIR_REQUIRE(x && out && n > 0, "iir_scale: bad args");
+  IIR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype), "iir_scale: unsupported dtype for this library build");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  scale_kernel<<<grid_for(n), 256, 0, st>>>(x, x_dtype == IIR_H16, out, out_dtype == IIR_H16, n, alpha);
+  count_launch();
+  return check_launch("iir_scale");
 }
 
 extern "C" int iir_timestep_embedding(const float* t, int n, int dim, void* out, int out_dtype,

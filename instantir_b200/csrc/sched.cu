@@ -113,6 +113,24 @@ cfg_rescale_kernel(const float* __restrict__ eu, const float* __restrict__ ec, f
   for (long long i = threadIdx.x; i < n_per; i += 1024) o[i] = (u[i] + g * (c[i] - u[i])) * factor;
 }
 
+// Start of one denoising step: latent_model_input = cat([latents] * n_rep) (scale_model_input is the identity for
+// DDPM), the timestep as a device scalar and the per-sample cond_scale (pipelines/sdxl_instantir.py:1503-1506,
+// 1538-1540) — one launch instead of two fills and n_rep copies, so that the captured graphs of the step read
+// static buffers and no torch op runs between them.
+__global__ void __launch_bounds__(256)
+step_prologue_kernel(const float* __restrict__ latents, long long n4, int n_rep, float* __restrict__ x_in, float t,
+                     float* __restrict__ t_dev, float cond_scale, float* __restrict__ cond_scale_dev, int n_cond) {
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0 && t_dev) t_dev[0] = t;
+    if (cond_scale_dev)
+      for (int i = threadIdx.x; i < n_cond; i += 256) cond_scale_dev[i] = cond_scale;
+  }
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    const float4 v = ld4(latents + i * 4);
+    for (int r = 0; r < n_rep; ++r) st4(x_in + (r * n4 + i) * 4, v);
+  }
+}
+
 int grid_for4(long long n4) {
   long long b = (n4 + 255) / 256;
   long long cap = 8LL * sm_count();
@@ -157,6 +175,17 @@ extern "C" int iir_cfg_ddpm_step(const void* eps_uncond, const void* eps_cond, i
         noise, prev, pred_x0, n / 4, guidance, sb, isa, c_x0, c_xt, sigma);
   count_launch();
   return check_launch("iir_cfg_ddpm_step");
+}
+
+extern "C" int iir_step_prologue(const float* latents, int64_t n, int n_rep, float* x_in, float t, float* t_dev,
+                                 float cond_scale, float* cond_scale_dev, int n_cond, void* stream) {
+  IIR_REQUIRE(latents && x_in && n > 0 && n % 4 == 0 && n_rep >= 1, "iir_step_prologue: bad args (n=%lld)", (long long)n);
+  IIR_REQUIRE(!cond_scale_dev || n_cond > 0, "iir_step_prologue: n_cond must be positive");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  step_prologue_kernel<<<grid_for4(n / 4), 256, 0, st>>>(latents, n / 4, n_rep, x_in, t, t_dev, cond_scale, cond_scale_dev,
+                                                          n_cond);
+  count_launch();
+  return check_launch("iir_step_prologue");
 }
 
 extern "C" int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n,

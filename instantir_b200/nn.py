@@ -22,7 +22,7 @@ from .weights import merge_lora
 class Runtime:
     """Execution mode shared by every layer of a model."""
 
-    def __init__(self, device, precision: str = "bf16"):
+    def __init__(self, device, precision: str = "fp16"):
         if precision not in ("bf16", "fp16", "fp32"):
             raise ValueError("precision must be 'bf16' / 'fp16' (tcgen05 path) or 'fp32' (check mode)")
         self.device = torch.device(device)
@@ -193,6 +193,7 @@ class SmallLinear:
         self.w = _load_w(rt, src, name)
         self.b = _bias(src, name)
         self.N, self.K = self.w.base.shape
+        self.in_features, self.out_features = self.K, self.N  # nn.Linear's names (pipelines/sdxl_instantir.py:973)
         self.bank, self.off = None, 0
         if bank is not None:
             bank.add(self)

@@ -54,10 +54,12 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _L(*tensors):
-    """the library build matching the 16-bit dtype of the call's tensors (bf16 build for pure-fp32 calls)"""
+    """the library build matching the 16-bit dtype of the call's tensors (the default build for pure-fp32 calls)"""
     for t in tensors:
         if t is not None and t.dtype == torch.float16:
             return _lib.load(h16=F16)
+        if t is not None and t.dtype == torch.bfloat16:
+            return _lib.load(h16=BF16)
     return _lib.load()
 
 
@@ -89,7 +91,17 @@ def _f32rows(t: Optional[torch.Tensor], name: str):
     return t, t.stride(0)
 
 
-N_SM = 148  # B200
+_N_SM = {}
+
+
+def n_sm() -> int:
+    """SM count of the current CUDA device (148 on a B200; also the answer on a GPU-less build box)"""
+    if not torch.cuda.is_available():
+        return 148
+    d = torch.cuda.current_device()
+    if d not in _N_SM:
+        _N_SM[d] = torch.cuda.get_device_properties(d).multi_processor_count
+    return _N_SM[d]
 
 
 def default_bn(n: int, pair: bool = False) -> int:
@@ -112,7 +124,7 @@ def choose_bn(M: int, N: int, K: int) -> int:
     best, best_cost = 256, None
     for bn in range(32, 257, 32):
         tn = (N + bn - 1) // bn
-        waves = (tm * tn + N_SM - 1) // N_SM
+        waves = (tm * tn + n_sm() - 1) // n_sm()
         # per 16-deep UMMA step: tensor pipe, smem operand reads (128 B/clk), L2->SM fill (~52 B/clk/SM;
         # the weight tile is split over a 2-CTA cluster and multicast, so each CTA pulls A + B/2)
         cyc = max(bn / 2.0, 32.0 + bn / 4.0, (4096.0 + bn * 16.0) / 52.0)
@@ -302,7 +314,7 @@ def adaln_items(entries, device) -> torch.Tensor:
 def adaln_batched(table: torch.Tensor, n_items: int, mod, out_dtype, *, rows: int, rows_per_sample: int,
                   eps: float = 1e-6, bytes_moved: float = 0.0):
     """every item's LN(x)*(1+scale)+shift in one launch (table from adaln_items)."""
-    lib = _lib.load(h16=F16) if out_dtype == torch.float16 else _lib.load()
+    lib = _lib.load(h16=F16) if out_dtype == torch.float16 else _lib.load(h16=BF16) if out_dtype == torch.bfloat16 else _lib.load()
     mod, mod_ld = _f32rows(mod, "mod")
     dt = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}[out_dtype]
     with _Prof("adaln_batched", bytes=bytes_moved):
@@ -358,6 +370,25 @@ def add(a, b, out):
     _lib.check(lib.iir_add(_p(a), _dt(a), _p(b), _dt(b), _p(out), _dt(out), out.numel(), _stream()),
                "iir_add", lib)
     return out
+
+
+def scale(x, out, alpha: float):
+    """out = alpha * x elementwise"""
+    lib = _L(x, out)
+    _lib.check(lib.iir_scale(_p(x), _dt(x), _p(out), _dt(out), out.numel(), float(alpha), _stream()), "iir_scale", lib)
+    return out
+
+
+def step_prologue(latents, x_in, n_rep: int, *, t: float, t_dev, cond_scale: float, cond_scale_dev):
+    """x_in = cat([latents] * n_rep); t_dev[0] = t; cond_scale_dev[:] = cond_scale — one launch at the top of a step"""
+    lib = _L()
+    _f32c(latents, "latents"), _f32c(x_in, "x_in"), _f32c(t_dev, "t_dev"), _f32c(cond_scale_dev, "cond_scale_dev")
+    if x_in.numel() != n_rep * latents.numel():
+        raise ValueError("step_prologue: x_in must hold n_rep copies of latents")
+    _lib.check(lib.iir_step_prologue(_p(latents), latents.numel(), n_rep, _p(x_in), float(t), _p(t_dev), float(cond_scale),
+                                     _p(cond_scale_dev), 0 if cond_scale_dev is None else cond_scale_dev.numel(), _stream()),
+               "iir_step_prologue", lib)
+    return x_in
 
 
 def timestep_embedding(t, dim: int, out):

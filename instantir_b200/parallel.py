@@ -49,6 +49,14 @@ class CFGParallel:
             if k == self.rank // 2:
                 self.group = g
 
+    def broadcast_from_leader(self, t: torch.Tensor) -> torch.Tensor:
+        """the uncond rank's tensor on both ranks of the pair (initial latents, DDPM noise: the two branches must
+        step identical x_t with identical z, whatever RNG state each process came with)"""
+        t = t.contiguous()
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else (self.rank // 2) * 2,
+                       group=self.group)
+        return t
+
     def gather_branches(self, eps: torch.Tensor) -> torch.Tensor:
         """[B,4,h,w] of this rank's branch -> [2B,4,h,w] = [uncond; cond] on both ranks of the pair."""
         eps = eps.contiguous()

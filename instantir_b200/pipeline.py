@@ -88,6 +88,8 @@ class _Graphed:
 
 
 class InstantIRPipeline:
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]  # pipelines/sdxl_instantir.py:301
+
     def __init__(self, unet, aggregator, scheduler, vae=None, text_encoder=None, text_encoder_2=None, tokenizer=None,
                  tokenizer_2=None, feature_extractor=None, image_encoder=None):
         self.unet, self.aggregator, self.scheduler = unet, aggregator, scheduler
@@ -166,6 +168,9 @@ class InstantIRPipeline:
         # dp_shard=(total_images, slice): this rank restores images[slice] of a data-parallel job; noise is
         # drawn for the FULL batch and sliced so the sharded run is bit-comparable with the unsharded one
         if dp_shard is not None:
+            if generator is None:
+                raise ValueError("dp_shard needs an explicitly seeded `generator` (identical on every rank): each rank draws the "
+                                 "full-batch noise and keeps its slice, which is only consistent when the streams agree")
             total_b, sl = dp_shard
 
             def draw(shape):
@@ -181,16 +186,32 @@ class InstantIRPipeline:
             # (the reference draws this sample from torch's global RNG; here from `generator`, before any other draw)
             image = self.vae.encode(image).latent_dist.sample(generator, scale=self.vae.config.scaling_factor)
         B, _, h, w = image.shape
-        H_px, W_px = height or h * 8, width or w * 8
+        # :1369,1381-1382: height / width are taken from the prepared image (the `height` / `width` arguments only
+        # steer the reference's PIL preprocessing, which tensors bypass)
+        H_px, W_px = h * 8, w * 8
         ts, num_inference_steps = retrieve_timesteps(sched, num_inference_steps, dev, timesteps)
         n = len(ts)
-        # 6. latents: LQ latent noised to t0 with the user's generator (:931-939, :1388-1389)
-        if latents is not None:
-            latents = latents.to(**f32).contiguous()
-        elif init_latents_with_lq:
+        # 6. latents (:1388-1401): the LQ latent noised to t0 with the user's generator (init_latents :931-939; a passed
+        # `latents` is ignored on this branch, as in the reference), else prepare_latents (:942-963)
+        if init_latents_with_lq:
             latents = sched.add_noise(image, draw(image.shape), ts[:1])
+        elif latents is not None:
+            latents = latents.to(**f32).contiguous() * sched.init_noise_sigma
         else:
             latents = draw(image.shape) * sched.init_noise_sigma
+        # DDPM variance noise of every step, drawn now in step order (the generator sees exactly the calls the
+        # reference's loop makes, :1629): no RNG launch is left inside the loop, and a CFG pair needs one broadcast
+        step_noise = [draw(latents.shape) if int(t) > 0 else None for t in ts]
+        if cfg_parallel is not None:
+            # both ranks of a pair MUST step with identical x_t and z: the pair leader's draws win,
+            # whatever generator state the other rank came with
+            image = cfg_parallel.broadcast_from_leader(image)
+            latents = cfg_parallel.broadcast_from_leader(latents)
+            live = [z for z in step_noise if z is not None]
+            if live:
+                stack = cfg_parallel.broadcast_from_leader(torch.stack(live))
+                it = iter(stack.unbind(0))
+                step_noise = [next(it) if z is not None else None for z in step_noise]
         keep, previewing = step_masks(n, preview_start, preview_end, control_guidance_start, control_guidance_end)
         scales = controlnet_conditioning_scale if isinstance(controlnet_conditioning_scale, list) else [controlnet_conditioning_scale] * n
         if len(scales) != n:
@@ -222,7 +243,8 @@ class InstantIRPipeline:
         # Static tensors + captured graphs are kept across calls of the same shape: new conditioning is
         # copied INTO the static buffers (version bump -> step-invariant caches recompute in place), so the
         # graphs captured for the first image are replayed for every later one.
-        key = (tuple(branches), B, h, w, bool(use_cuda_graph), tuple((k, tuple(v.shape)) for k, v in sorted(new.items())))
+        key = (tuple(branches), B, h, w, bool(use_cuda_graph), bool(overlap_streams), bool(agg_ahead), agg.weights_version,
+               tuple((k, tuple(v.shape)) for k, v in sorted(new.items())))
         S = self._graphs.get(key)
         if S is None:
             S = SimpleNamespace(**{k: v.contiguous().clone() for k, v in new.items()})
@@ -360,11 +382,9 @@ class InstantIRPipeline:
             """one denoising step of the schedule (pipelines/sdxl_instantir.py:1497-1666)."""
             t_int = int(ts[i])
             lat = loop.latents
-            t_dev.fill_(float(t_int))
-            for k in range(len(branches)):
-                x_in[k * B:(k + 1) * B].copy_(lat)  # torch.cat([latents]*2) (:1503); scale_model_input = id
             cs = min(1.0, float(scales[i])) * keep[i]  # preview_factor == 1 without adastep_restore
-            cond_scale.fill_(cs)
+            # torch.cat([latents]*2) (:1503; scale_model_input = id), t and cond_scale (:1538-1540) in ONE launch
+            ops.step_prologue(lat, x_in, len(branches), t=float(t_int), t_dev=t_dev, cond_scale=cs, cond_scale_dev=cond_scale)
             previewed = False
             noise_pred = None
             if cs > 0.1:  # the `(cond_scale>0.1).sum().item() > 0` gate (:1542), decided on the host
@@ -372,7 +392,8 @@ class InstantIRPipeline:
                     preview_noise = g_preview()
                     previewer_scheduler.step(preview_noise, t_int, x_in, return_dict=False, out=preview_latent)
                     previewed = True
-                    if save_preview_row:
+                    # the reference keeps the cond chunk (:1564-1567); in a CFG pair only the cond rank holds it
+                    if save_preview_row and (cfg_parallel is None or cfg_parallel.branch == 1):
                         loop.preview_row.append(preview_latent[-B:].clone())
                     loop.res_src = "prev"
                 else:
@@ -422,7 +443,7 @@ class InstantIRPipeline:
                 g_step_arg = None
             out = sched.step(noise_pred, t_int, lat, generator=generator, return_dict=True,
                              guidance=g_step_arg,
-                             noise=draw(lat.shape) if t_int > 0 else None)
+                             noise=step_noise[i])
             loop.latents = out.prev_sample
             if record is not None:
                 record.setdefault("latents", []).append(loop.latents.clone())
@@ -435,13 +456,28 @@ class InstantIRPipeline:
             return loop
         callback_on_step_end = kwargs.get("callback_on_step_end")
         callback, callback_steps = kwargs.get("callback"), kwargs.get("callback_steps") or 1
+        names = kwargs.get("callback_on_step_end_tensor_inputs", ["latents"])
+        bad = [k for k in names if k not in self._callback_tensor_inputs]
+        if bad:  # check_inputs, :774-779
+            raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but found {bad}")
+        nbr = len(branches)
         for i in range(n):
             step(i)
-            if callback_on_step_end is not None:  # :1650-1658: the callback may replace the latents
-                names = kwargs.get("callback_on_step_end_tensor_inputs", ["latents"])
-                avail = {"latents": loop.latents, "prompt_embeds": prompt_embeds, "negative_prompt_embeds": negative_prompt_embeds}
+            if callback_on_step_end is not None:
+                # :1650-1658.  Inside the reference's loop `prompt_embeds` is the CFG-concatenated tensor the UNet reads;
+                # whatever the callback returns replaces it for the following steps (here: copied into the static
+                # conditioning buffer, step-invariant K/V recomputed in place)
+                avail = {"latents": loop.latents, "prompt_embeds": S.prompt_all, "negative_prompt_embeds": negative_prompt_embeds}
                 outputs = callback_on_step_end(self, i, ts[i], {k: avail[k] for k in names}) or {}
-                loop.latents = outputs.pop("latents", loop.latents)
+                loop.latents = outputs.pop("latents", loop.latents).to(**f32).contiguous()
+                new_pe = outputs.pop("prompt_embeds", None)
+                outputs.pop("negative_prompt_embeds", None)  # rebinds a name the reference's loop never reads again
+                if new_pe is not None and new_pe is not S.prompt_all:
+                    if tuple(new_pe.shape) != tuple(S.prompt_all.shape):
+                        raise ValueError(f"callback returned prompt_embeds of shape {tuple(new_pe.shape)}, expected "
+                                         f"{tuple(S.prompt_all.shape)} ({nbr} CFG branch(es) x batch)")
+                    S.prompt_all.copy_(new_pe.to(**f32))
+                    unet.refresh_context(S.prompt_all, S.added, None)
             if callback is not None and i % callback_steps == 0:  # deprecated form (:1660-1664)
                 callback(i // getattr(sched, "order", 1), ts[i], loop.latents)
         latents, preview_row = loop.latents, loop.preview_row

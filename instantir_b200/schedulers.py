@@ -31,6 +31,26 @@ def _randn(shape, generator, device):
     return torch.randn(shape, generator=generator, dtype=torch.float32, device=device)
 
 
+def _add_noise(alphas_cumprod, original_samples, noise, timesteps):
+    """sqrt(abar_t) x0 + sqrt(1 - abar_t) noise with abar indexed PER SAMPLE (lcm_single_step_scheduler.py:492-513; same
+    code in diffusers' DDPMScheduler): one launch when every sample shares the timestep (the pipeline's case,
+    pipelines/sdxl_instantir.py:931-939), one per sample otherwise."""
+    ts = torch.as_tensor(timesteps).reshape(-1).tolist()
+    x0, z = original_samples.float().contiguous(), noise.float().contiguous()
+    B = x0.shape[0]
+    if len(ts) == 1:
+        ts = ts * B
+    if len(ts) != B:
+        raise ValueError(f"add_noise: {len(ts)} timesteps for a batch of {B}")
+    out = torch.empty_like(x0)
+    if all(t == ts[0] for t in ts):
+        ops.add_noise(x0, z, out, alpha_prod_t=float(alphas_cumprod[int(ts[0])]))
+    else:
+        for b, t in enumerate(ts):
+            ops.add_noise(x0[b], z[b], out[b], alpha_prod_t=float(alphas_cumprod[int(t)]))
+    return out
+
+
 class LCMSingleStepScheduler:
     order = 1
 
@@ -74,13 +94,7 @@ class LCMSingleStepScheduler:
         return SimpleNamespace(denoised=out) if return_dict else (out,)
 
     def add_noise(self, original_samples, noise, timesteps):
-        ts = torch.as_tensor(timesteps).reshape(-1)
-        if not bool((ts == ts[0]).all()):
-            raise NotImplementedError("per-sample timesteps in add_noise (the pipeline uses one timestep, :931-939)")
-        out = torch.empty_like(original_samples, dtype=torch.float32)
-        ops.add_noise(original_samples.float().contiguous(), noise.float().contiguous(), out,
-                      alpha_prod_t=float(self.alphas_cumprod[int(ts[0])]))
-        return out
+        return _add_noise(self.alphas_cumprod, original_samples, noise, timesteps)
 
 
 class DDPMScheduler:
@@ -175,8 +189,4 @@ class DDPMScheduler:
         return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
     def add_noise(self, original_samples, noise, timesteps):
-        ts = torch.as_tensor(timesteps).reshape(-1)
-        out = torch.empty_like(original_samples, dtype=torch.float32)
-        ops.add_noise(original_samples.float().contiguous(), noise.float().contiguous(), out,
-                      alpha_prod_t=float(self.alphas_cumprod[int(ts[0])]))
-        return out
+        return _add_noise(self.alphas_cumprod, original_samples, noise, timesteps)

@@ -240,7 +240,7 @@ class _EmbeddingMixin:
 
 
 class UNet2DConditionModel(_EmbeddingMixin):
-    def __init__(self, cfg: ModelConfig, source, device="cuda", precision="bf16", adapter: bool = True):
+    def __init__(self, cfg: ModelConfig, source, device="cuda", precision="fp16", adapter: bool = True):
         self.cfg, self.source = cfg, source
         self.rt = rt = Runtime(device, precision)
         ch = cfg.block_out_channels

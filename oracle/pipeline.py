@@ -36,7 +36,8 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                     ip_image_embeds, add_time_ids, num_inference_steps=30, guidance_scale=7.0,
                     preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                     controlnet_conditioning_scale=1.0, generator=None, init_latents_with_lq=True,
-                    timesteps=None, record: Optional[dict] = None, guidance_rescale: float = 0.0):
+                    timesteps=None, record: Optional[dict] = None, guidance_rescale: float = 0.0,
+                    max_steps: Optional[int] = None):
     """Returns the final latents [B,4,h,w]; `record` (if given) collects per-step tensors.
 
     image: LQ latent [B,4,h,w] (the reference accepts 4-channel tensors as latents, :1370-1382).
@@ -67,6 +68,8 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
     preview_factor = torch.ones((latents.shape[0], 1, 1, 1), dtype=latents.dtype)
     down_res = mid_res = None
     for i, t in enumerate(ts):
+        if max_steps is not None and i >= max_steps:  # tests: only the first steps of a long schedule
+            break
         x_in = torch.cat([latents] * 2) if do_cfg else latents
         x_in = scheduler.scale_model_input(x_in, t)
         added = {"text_embeds": add_text_embeds, "time_ids": time_ids, "image_embeds": image_embeds}

@@ -137,6 +137,10 @@ lat = out[:3] + 7.0 * (out[3:] - out[:3]) + z
 ref = [torch.empty_like(lat) for _ in range(2)]
 dist.all_gather(ref, lat)
 assert torch.equal(ref[0], ref[1])
+# ranks that arrive with DIFFERENT generator states still step identical noise: the pair leader's draw wins
+mine_z = torch.randn(3, 4, 2, 2, generator=torch.Generator().manual_seed(100 + dist.get_rank()))
+want_z = torch.randn(3, 4, 2, 2, generator=torch.Generator().manual_seed(100))
+assert torch.equal(cp.broadcast_from_leader(mine_z), want_z)
 sl, br = parallel.partition(5, 2, dist.get_rank(), cfg_parallel=False)
 full = torch.randn(5, 4, generator=torch.Generator().manual_seed(1))
 mine = parallel.draw_shared_noise((5, 4), torch.Generator().manual_seed(1), "cpu", sl)

@@ -1,7 +1,9 @@
 """Model-level parity on the GPU, through the reference-shaped Python API which calls the C ABI.
 
-Tolerances are the north star's: relative L2 <= 1e-4 in the fp32 check mode, <= 1e-2 in bf16 for
-per-step latents (module outputs in bf16 get 2e-2: they are not yet damped by the scheduler step).
+Tolerances are the north star's: per-step latent relative L2 <= 1e-4 in the fp32 check mode and <= 1e-2 in the
+headline 16-bit precision, which is fp16 (the reference's own, infer.py:119).  bf16 misses that bar at CFG 7 and is
+tested as out of spec (xfail at 1e-2 + a regression envelope).  Single-module outputs (not yet damped by the
+scheduler step) get 3e-3 in fp16 and 2e-2 in bf16.
 Golden comparisons use vectors produced by running the reference's own files (tests/golden)."""
 import os
 
@@ -134,15 +136,28 @@ def test_full_step_config1_fp32_check_mode(precision, graph):
     assert rel_l2(out, ref) < 1e-4
 
 
+BF16_OUT_OF_SPEC = ("bf16 operands are OUT OF SPEC for the north star's <= 1e-2 per-step latent bar at CFG 7 (measured 1.4e-2 on the "
+                   "30-step spacing, 2.5e-2 on config 1's 2-step schedule): 8-bit-mantissa rounding through ~60 sequential GEMM stages "
+                   "gives ~1.2e-2 per branch, which CFG 7 amplifies (DESIGN.md §4).  The headline precision is fp16 (the reference's "
+                   "own, infer.py:119), which meets the bar; precision='bf16' remains available and is reported as out of spec.")
+
+
+@pytest.mark.xfail(reason=BF16_OUT_OF_SPEC, strict=False)
 @pytest.mark.parametrize("graph", [False, True])
 def test_full_step_bf16_on_30_step_spacing(graph):
-    """bf16 tcgen05 path on the first steps of the real 30-step schedule (t = 958, 925 -> prev 925, 892),
-    CFG 7, vs the fp32 oracle.  KNOWN GAP: the north star asks <= 1e-2; measured
-    1.4e-2.  The per-branch eps error (~1.2e-2) is the bf16-operand rounding floor of a network this deep
-    (the fp32 check mode of the same graph is at 3e-6) and CFG-7 multiplies uncorrelated branch errors by
-    sqrt(7²+6²) ~ 9.  The bound asserted here is 2e-2; the reference itself runs fp16 (8x finer mantissa).
-    A third timestep is listed only so that 925's predecessor is 892 as in the 30-step run."""
+    """bf16 tcgen05 path on the first steps of the real 30-step schedule (t = 958, 925 -> prev 925, 892), CFG 7, vs the
+    fp32 oracle, held to the north star's 1e-2: an expected failure, kept so the gap stays measured (not hidden behind a
+    widened tolerance).  A third timestep is listed only so that 925's predecessor is 892 as in the 30-step run."""
     ref, rec_o, out, rec_p = _run_pair("bf16", graph=graph, timesteps=[958, 925, 892])
+    errs = [rel_l2(rec_p["latents"][i], rec_o["latents"][i]) for i in range(2)]
+    print("bf16 per-step latent rel L2:", errs)
+    assert max(errs) < 1e-2, errs
+
+
+def test_bf16_stays_within_its_measured_envelope():
+    """bf16 is out of spec, but it must not drift further: 2e-2 on the 30-step spacing (regression guard, NOT a parity
+    claim — parity is claimed for fp16 and the fp32 check mode only)."""
+    ref, rec_o, out, rec_p = _run_pair("bf16", graph=True, timesteps=[958, 925, 892])
     for i in range(2):
         assert rel_l2(rec_p["latents"][i], rec_o["latents"][i]) < 2e-2, f"step {i}"
 
@@ -170,12 +185,14 @@ def test_bf16_without_cfg_amplification_meets_1e2():
         assert rel_l2(rec_p["latents"][i], rec_o["latents"][i]) < 1e-2, f"step {i}"
 
 
+@pytest.mark.xfail(reason=BF16_OUT_OF_SPEC, strict=False)
 def test_full_step_config1_bf16_coarse_schedule():
-    """config 1's own 2-step schedule (t = 501, 1) in bf16.  The 500-timestep jump multiplies the eps
-    error by d x_prev / d eps = 1.62 (0.37 on the 30-step spacing): bound 5e-2, see DESIGN.md §parity."""
+    """config 1's own 2-step schedule (t = 501, 1) in bf16, held to 1e-2: expected failure (the 500-timestep jump
+    multiplies the eps error by d x_prev / d eps = 1.62, against 0.37 on the 30-step spacing)."""
     ref, rec_o, out, rec_p = _run_pair("bf16", graph=True)
-    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
-        assert rel_l2(a, b) < 5e-2, f"step {i}"
+    errs = [rel_l2(a, b) for a, b in zip(rec_p["latents"], rec_o["latents"])]
+    print("bf16 config-1 per-step latent rel L2:", errs)
+    assert max(errs) < 1e-2, errs
 
 
 def test_batch_of_two_images_fp32():
@@ -296,7 +313,81 @@ def test_guidance_scale_le_1_disables_cfg_fp32():
     assert rel_l2(out, ref) < 1e-4
 
 
-# ------------------------------------------------------------------ full size (BASELINE config 2)
+# ------------------------------------------------------------------ SDXL widths (BASELINE configs 2-5)
+def _device_seeded_init(module, seed, scale_keys=()):
+    """seeding.seeded_init's distribution, drawn on the GPU (4.4 G parameters in seconds instead of minutes on the host)
+    and copied into the CPU oracle module; returns the same tensors as a device state dict for the product."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    sd = {}
+    for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
+        t = torch.randn(p.shape, generator=g, device=DEV, dtype=torch.float32)
+        if p.ndim >= 2:
+            t.mul_(p[0].numel() ** -0.5)
+        else:
+            t.mul_(0.05)
+            if "norm" in name and name.endswith("weight"):
+                t.add_(1.0)
+        if any(name.startswith(k[0]) and name.endswith(k[1]) for k in scale_keys):
+            t.mul_(0.5)
+        p.data.copy_(t)
+        sd[name] = t
+    return sd
+
+
+@pytest.fixture(scope="module")
+def sdxl_width_oracle_step():
+    """ONE UNet + Aggregator step (BASELINE config 2's shape: previewer off, CFG 7, first step of the 30-step schedule,
+    t = 958 -> 925) of the CPU oracle at FULL SDXL widths (2.57 G + 1.0 G parameters, IP-adapter processors and
+    Resampler installed), latent 32x32 so that the fp32 CPU run takes seconds."""
+    oc = ocfg.sdxl()
+    with torch.device("meta"):
+        ounet = om.load_adapter(om.UNet2DConditionModel(oc))
+        oagg = om.Aggregator(oc)
+        om.remove_attn2(oagg)
+    ounet.to_empty(device="cpu")
+    oagg.to_empty(device="cpu")
+    sd_u = _device_seeded_init(ounet, 0)
+    # keep the injected residuals O(1) relative to the skips they are added to (as _util.build_oracle does)
+    sd_a = _device_seeded_init(oagg, 1, scale_keys=[("controlnet_down_blocks.", ".1.weight"), ("controlnet_mid_block.1", "weight")])
+    inp = make_inputs(oc, B=1, h=32, w=32)
+    rec = {}
+    opipe.restore_latents(
+        ounet.eval(), oagg.eval(), osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"],
+        prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+        pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+        ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], num_inference_steps=30, guidance_scale=7.0,
+        preview_start=1.0, generator=torch.Generator().manual_seed(42), record=rec, max_steps=1)
+    del ounet, oagg
+    return dict(cfg=oc, inp=inp, sd_u=sd_u, sd_a=sd_a, latents=rec["latents"][0], pred_x0=rec["pred_x0"][0])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-2), ("fp32", 1e-4)])
+def test_sdxl_width_step_vs_oracle(sdxl_width_oracle_step, precision, tol):
+    """The product's UNet + Aggregator step at SDXL widths against the CPU ORACLE on the same weights, seeds and
+    inputs (not against another mode of the product): per-step latent relative L2 <= 1e-2 in the headline precision
+    (fp16 operands on the tcgen05 path) and <= 1e-4 in the fp32 check mode — the north star's bar, at the widths,
+    head counts, GEMM / conv shapes and tile choices of BASELINE configs 2-5 (latent 32x32: M = 2048 ... 128 rows)."""
+    o = sdxl_width_oracle_step
+    pc = _pcfg_from(o["cfg"])
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(o["sd_u"], DEV), DEV, precision)
+    agg = Aggregator(pc, weights.StateDictSource(o["sd_a"], DEV), DEV, precision)
+    pipe = InstantIRPipeline(unet, agg, DDPMScheduler())
+    inp, rec = o["inp"], {}
+    loop = pipe(image=inp["image"], prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
+                ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=30, guidance_scale=7.0,
+                previewer_scheduler=LCMSingleStepScheduler(), preview_start=1.0, generator=torch.Generator().manual_seed(42),
+                record=rec, prepare_only=True)
+    loop.step(0)
+    torch.cuda.synchronize()
+    e_lat, e_x0 = rel_l2(rec["latents"][0], o["latents"]), rel_l2(rec["pred_x0"][0], o["pred_x0"])
+    print(f"SDXL-width step vs oracle [{precision}]: latents {e_lat:.3e}, pred_x0 (guided eps) {e_x0:.3e}")
+    assert e_lat < tol
+    assert e_x0 < (5e-2 if precision == "fp16" else 5e-4)  # x0 = (x - sqrt(1-abar) eps)/sqrt(abar): eps error / 0.087 at t = 958
+    del unet, agg, pipe, loop
+    torch.cuda.empty_cache()
+
+
 def _full_models(precision):
     import bench
 
@@ -304,14 +395,15 @@ def _full_models(precision):
     return bench.build_models(cfg, DEV, precision, with_lora=False), cfg
 
 
-def test_full_size_1024_bf16_vs_fp32_check_mode_and_invariants():
-    """At BASELINE's full size (SDXL widths, 1024² -> latent 128², CFG batch 2) the CPU oracle is too slow, so
-    parity is carried by size-independent properties on identical random-init weights:
-      (1) the bf16 tcgen05 path agrees with the fp32 check mode (itself oracle-exact at small size) on the
-          aggregator residuals and on eps of one UNet+aggregator step;
-      (2) residuals scaled by cond_scale = 0 leave eps bit-identical to the no-residual forward
+def test_full_size_1024_invariants_and_fp32_check_mode():
+    """At BASELINE's full size (SDXL widths, 1024² -> latent 128², CFG batch 2) the CPU oracle needs minutes (the oracle
+    comparison at SDXL widths is test_sdxl_width_step_vs_oracle, at latent 32²), so this test adds the size-independent
+    properties on identical random-init weights:
+      (1) residuals scaled by cond_scale = 0 leave eps bit-identical to the no-residual forward
           (pipelines/sdxl_instantir.py:1602-1603: stale residuals x 0);
-      (3) the same launch sequence is bit-deterministic."""
+      (2) the same launch sequence is bit-deterministic;
+      (3) supplementary: the fp16 tcgen05 path agrees with the fp32 check mode (oracle-exact in the test above) on the
+          aggregator residuals and on eps of one UNet+aggregator step at the full 128² size."""
     import bench
 
     cfg = pcfg.sdxl()
@@ -325,12 +417,12 @@ def test_full_size_1024_bf16_vs_fp32_check_mode_and_invariants():
              "image_embeds": [torch.cat([host["ip_adapter_image_embeds"][0], host["ip_adapter_image_embeds"][1]]).unsqueeze(1).to(DEV)]}
     img = torch.cat([host["image"]] * 2).to(DEV)
     res = {}
-    for prec in ("bf16", "fp32"):
+    for prec in ("fp16", "fp32"):
         (unet, agg), _ = _full_models(prec)
         down, mid = agg(img, t, text, controlnet_cond=x, added_cond_kwargs=added)
         eps = unet(x, t, text, added_cond_kwargs=added, down_block_additional_residuals=down,
                    mid_block_additional_residual=mid)[0]
-        if prec == "bf16":
+        if prec == "fp16":
             eps2 = unet(x, t, text, added_cond_kwargs=added, down_block_additional_residuals=down,
                         mid_block_additional_residual=mid)[0]
             assert torch.equal(eps, eps2), "not deterministic"
@@ -344,9 +436,9 @@ def test_full_size_1024_bf16_vs_fp32_check_mode_and_invariants():
         res[prec] = ([d.float().cpu() for d in down], mid.float().cpu(), eps.float().cpu())
         del unet, agg
         torch.cuda.empty_cache()
-    assert bool(torch.isfinite(res["bf16"][2]).all())
-    errs = [rel_l2(a, b) for a, b in zip(res["bf16"][0], res["fp32"][0])] + [rel_l2(res["bf16"][1], res["fp32"][1])]
-    assert max(errs) < 5e-2, errs
-    e = rel_l2(res["bf16"][2], res["fp32"][2])
-    print(f"full-size eps rel L2 bf16 vs fp32 check mode: {e:.3e}; aggregator residuals max {max(errs):.3e}")
-    assert e < 5e-2
+    assert bool(torch.isfinite(res["fp16"][2]).all())
+    errs = [rel_l2(a, b) for a, b in zip(res["fp16"][0], res["fp32"][0])] + [rel_l2(res["fp16"][1], res["fp32"][1])]
+    e = rel_l2(res["fp16"][2], res["fp32"][2])
+    print(f"full-size eps rel L2 fp16 vs fp32 check mode: {e:.3e}; aggregator residuals max {max(errs):.3e}")
+    assert max(errs) < 5e-3, errs
+    assert e < 5e-3

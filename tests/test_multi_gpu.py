@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 def test_cfg_parallel_and_dp_match_single_gpu(precision):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ, NCCL_DEBUG="WARN")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541" if precision == "fp32" else "29542",
+                        "--master-addr", "127.0.0.1", "--master-port", {"fp32": "29541", "fp16": "29542", "bf16": "29543"}[precision],
                         os.path.join(ROOT, "tools", "cfgp_check.py"), precision],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

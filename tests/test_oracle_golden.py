@@ -161,7 +161,7 @@ def test_vae_decoder_vs_reference_run():
     the reference's AttnProcessor2_0 in the mid block (tests/golden/make_golden_vae.py); SDXL VAE parameter count."""
     from oracle import vae as ov
 
-    g = torch.load(os.path.join(G, "vae_decoder.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "vae_decoder.pt"))
     cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
     dec = ov.Decoder(cfg)
     assert sorted(k for k, _ in dec.named_parameters()) == g["names"]
@@ -180,7 +180,7 @@ def test_vae_encoder_and_distribution_vs_reference_run():
     """oracle Encoder vs the reference's Encoder.forward run verbatim; DiagonalGaussianDistribution sample / mode"""
     from oracle import vae as ov
 
-    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "vae_encoder.pt"))
     cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
     enc = ov.Encoder(cfg)
     assert sorted(k for k, _ in enc.named_parameters()) == g["names"]
@@ -198,7 +198,7 @@ def test_rescale_noise_cfg_vs_reference_run():
     """oracle.pipeline.rescale_noise_cfg vs the reference's own function executed verbatim (make_golden_misc.py)"""
     from oracle import pipeline as opipe
 
-    g = torch.load(os.path.join(G, "rescale_noise_cfg.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "rescale_noise_cfg.pt"))
     cfg = g["e_u"] + g["guidance"] * (g["e_c"] - g["e_u"])
     for phi, want in g["out"].items():
         assert torch.equal(opipe.rescale_noise_cfg(cfg, g["e_c"], phi), want), phi

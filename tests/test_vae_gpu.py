@@ -39,7 +39,7 @@ def _oracle_vae(cfg, seed=71):
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2), ("fp16", 4e-3)])
 def test_decoder_vs_reference_run_vector(precision, tol):
     """product Decoder vs the vector produced by the reference's own Decoder.forward (tests/golden/make_golden_vae.py)"""
-    g = torch.load(os.path.join(G, "vae_decoder.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "vae_decoder.pt"))
     cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
     odec = ov.Decoder(cfg)
     seeded_init(odec, g["seed"])
@@ -71,7 +71,13 @@ def test_autoencoder_decode_vs_oracle(precision, tol):
         vae.decode(torch.zeros(1, 3, 8, 8, device=DEV))
 
 
-@pytest.mark.parametrize("precision,min_psnr,preview_start", [("fp32", 60.0, 0.0), ("fp16", 40.0, 0.0), ("bf16", 40.0, 1.0)])
+_BF16_XFAIL = pytest.mark.xfail(strict=False, reason="bf16 is out of spec for the north star's parity bars at CFG 7 (DESIGN.md §4); "
+                                "the headline precision is fp16")
+
+
+@pytest.mark.parametrize("precision,min_psnr,preview_start", [
+    ("fp32", 60.0, 0.0), ("fp16", 40.0, 0.0), ("fp16", 40.0, 1.0),
+    pytest.param("bf16", 40.0, 0.0, marks=_BF16_XFAIL), ("bf16", 40.0, 1.0)])
 def test_pipeline_decoded_image_psnr_vs_oracle(precision, min_psnr, preview_start):
     """BASELINE config 1 end to end: denoising loop + VAE decode through the public API (output_type='pt') against the
     oracle loop + oracle VAE on the same weights and seeds.  North star: decoded-image PSNR >= 40 dB."""
@@ -158,7 +164,7 @@ def test_encoder_vs_reference_run_vector(precision, tol):
     convs padded bottom/right only, one-head mid attention on a 8x6 grid, 8-channel conv_out"""
     from instantir_b200.vae import vae_param_shapes
 
-    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "vae_encoder.pt"))
     cfg = ov.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
     ovae = _full_oracle_vae(cfg)
     seeded_init(ovae.encoder, g["seed"])
@@ -180,7 +186,7 @@ def test_gaussian_distribution_vs_reference_run_vector():
     from instantir_b200 import ops
     from instantir_b200.vae import DiagonalGaussianDistribution
 
-    g = torch.load(os.path.join(G, "vae_encoder.pt"), weights_only=False)
+    g = torch.load(os.path.join(G, "vae_encoder.pt"))
     m, noise = g["moments"].to(DEV), g["noise"].to(DEV).contiguous()
     m[0, 4:, 0, 0] = 50.0   # logvar above the clamp at 20
     m[1, 4:, 1, 1] = -80.0  # and below the clamp at -30
@@ -197,7 +203,7 @@ def test_gaussian_distribution_vs_reference_run_vector():
     assert rel_l2(s, 0.5 * ov.gaussian_sample(g["moments"], n9)) < 1e-6
 
 
-@pytest.mark.parametrize("precision,min_psnr", [("fp32", 60.0), ("bf16", 38.0)])
+@pytest.mark.parametrize("precision,min_psnr", [("fp32", 60.0), ("fp16", 40.0), pytest.param("bf16", 40.0, marks=_BF16_XFAIL)])
 def test_pipeline_from_pixels_to_pixels_psnr_vs_oracle(precision, min_psnr):
     """the whole f1 row around the loop: a 3-channel image in [-1, 1] -> vae.encode -> sample * scaling_factor ->
     2 denoising steps (previewer off) -> vae.decode -> image, against the oracle doing the same with the same draws"""

@@ -33,7 +33,9 @@ kw = dict(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negati
 full = pipe(image=inp["image"], ip_adapter_image_embeds=[inp["ip"]], generator=torch.Generator().manual_seed(42), **kw).images
 # --- CFG-parallel: both ranks hold all B images, each runs one branch
 cp = parallel.CFGParallel()
-out = pipe(image=inp["image"], ip_adapter_image_embeds=[inp["ip"]], generator=torch.Generator().manual_seed(42),
+# the cond rank arrives with a DIFFERENT generator state (and, second call, with none at all): the pair leader's
+# draws are broadcast, so the result must still equal the single-GPU run seeded 42
+out = pipe(image=inp["image"], ip_adapter_image_embeds=[inp["ip"]], generator=torch.Generator().manual_seed(42 + 1000 * rank),
            cfg_parallel=cp, **kw).images
 e_cfgp = rel_l2(out, full)
 # --- data parallel: rank r restores image r of the batch, drawing the full-batch noise and slicing
@@ -46,6 +48,6 @@ res = torch.tensor([e_cfgp, e_dp], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"MULTI_GPU_CHECK precision={prec} cfg_parallel_vs_single={float(res[0]):.3e} dp_shard_vs_batched={float(res[1]):.3e}")
-    tol = 1e-5 if prec == "fp32" else 2e-2  # bf16: different batch partition -> different tiles/rounding
+    tol = 1e-5 if prec == "fp32" else 2e-2 if prec == "bf16" else 5e-3  # 16-bit: different batch partition -> different tiles/rounding
     assert float(res[0]) < tol and float(res[1]) < tol
 dist.barrier(); dist.destroy_process_group()

@@ -476,13 +476,21 @@ def run_ours(args):
             loop2.step(2)                    # the replay whose events are read
             torch.cuda.synchronize()
             ops.PROFILE = captured
+        shapes = {}
         if loop2 is not None:
             for name, work, a, b in ops.PROFILE:
                 d = breakdown.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+                dt_ms = a.elapsed_time(b)
                 d["launches"] += 1
-                d["ms"] += a.elapsed_time(b)
+                d["ms"] += dt_ms
                 d["flops"] += work.get("flops", 0.0)
                 d["bytes"] += work.get("bytes", 0.0)
+                if "key" in work or "n_kv" in work:  # per-shape view of the tensor-core launches
+                    k = work.get("key") or f"attn:{work['n_q']}x{work['n_kv']}"
+                    sh = shapes.setdefault(f"{name}:{k}", {"launches": 0, "ms": 0.0, "flops": 0.0})
+                    sh["launches"] += 1
+                    sh["ms"] += dt_ms
+                    sh["flops"] += work.get("flops", 0.0)
             ops.PROFILE = None
             del pipe2
             loop2 = None
@@ -528,6 +536,9 @@ def run_ours(args):
             "step_frac_of_sustained_peak": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12 / world / peak_sus) if step_flops else None,
             "partitions": partitions,
             "kernel_breakdown": breakdown,
+            # the 16 tensor-core shapes that take the most time in one step (key = kind:M:N:K:paired:epilogue)
+            "top_shapes": {k: dict(v, us_per_launch=1e3 * v["ms"] / v["launches"], tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None)
+                           for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:16]},
         }
         alt = "bf16" if args.precision == "fp16" else "fp16"
         if world == 1 and not args.no_alt:

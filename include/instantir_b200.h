@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 8
+#define IIR_ABI_VERSION 9
 
 typedef enum {
   IIR_OK = 0,
@@ -138,8 +138,14 @@ typedef struct {
   int dtype;            /* IIR_BF16 (tc) or IIR_F32/IIR_BF16 (simt), all tensors           */
   int B, heads, n_q;
   float softmax_scale;  /* 1/sqrt(64) (Resampler: also 1/8 = (64^-1/4)^2, resampler.py:71-72) */
+  /* optional (tc, one segment): scratch that lets the kernel balance work at key-block granularity — a query tile cut
+   * by a CTA boundary parks its partial (O, max, sum) there and the last part to arrive merges them.  At least
+   * iir_attn_workspace_bytes(B, heads, n_q) bytes, 256-byte aligned, ZERO before the first use (every launch leaves its
+   * ticket words zero again); launches that may run concurrently need distinct workspaces.  NULL = whole tiles per CTA. */
+  void* workspace; int64_t workspace_bytes;
 } iir_attn_args;
 
+int64_t iir_attn_workspace_bytes(int B, int heads, int n_q);
 int iir_attn_tc(const iir_attn_args* args, void* stream);
 int iir_attn_simt(const iir_attn_args* args, void* stream);
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 F32, BF16, F16 = 0, 1, 2
 # 16-bit operand type of the default library build: IEEE fp16 is the reference's own inference precision
 # (infer.py:119) and the one that meets the north star's <= 1e-2 per-step latent bar; the bf16
@@ -26,7 +26,7 @@ PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
 SYMBOLS = [
     "iir_abi_version", "iir_h16_dtype", "iir_last_error", "iir_launch_count",
     "iir_gemm_tc", "iir_gemm_simt", "iir_conv3x3_direct",
-    "iir_attn_tc", "iir_attn_simt",
+    "iir_attn_workspace_bytes", "iir_attn_tc", "iir_attn_simt",
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add", "iir_scale",
     "iir_timestep_embedding", "iir_linear_small",
@@ -72,6 +72,7 @@ class AttnArgs(C.Structure):
         ("dtype", C.c_int),
         ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int),
         ("softmax_scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -92,6 +93,8 @@ def _declare(lib):
     lib.iir_gemm_tc.argtypes = [C.POINTER(GemmArgs), vp]
     lib.iir_gemm_simt.argtypes = [C.POINTER(GemmArgs), vp]
     lib.iir_conv3x3_direct.argtypes = [vp, i, i, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.iir_attn_workspace_bytes.argtypes = [i, i, i]
+    lib.iir_attn_workspace_bytes.restype = i64
     lib.iir_attn_tc.argtypes = [C.POINTER(AttnArgs), vp]
     lib.iir_attn_simt.argtypes = [C.POINTER(AttnArgs), vp]
     lib.iir_groupnorm_scratch_floats.argtypes = [i, i]

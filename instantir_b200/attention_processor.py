@@ -174,7 +174,7 @@ class AttnProcessor2_0:
         if encoder_hidden_states is None:
             qkv = attn.to_qkv(hs, M)
             ops.attention(qkv, 0, 3 * C, [qkv], [C], [3 * C], [qkv], [2 * C], [3 * C], [n], [1.0], o, 0, C,
-                          B=B, heads=attn.heads, n_q=n, softmax_scale=SOFTMAX_SCALE, tc=rt.tc)
+                          B=B, heads=attn.heads, n_q=n, softmax_scale=SOFTMAX_SCALE, tc=rt.tc, scratch_owner=id(rt))
         else:
             if isinstance(encoder_hidden_states, tuple):
                 encoder_hidden_states = encoder_hidden_states[0]
@@ -182,7 +182,7 @@ class AttnProcessor2_0:
             kv = attn.text_kv(encoder_hidden_states)
             nt = encoder_hidden_states.shape[1]
             ops.attention(q, 0, C, [kv], [0], [2 * C], [kv], [C], [2 * C], [nt], [1.0], o, 0, C,
-                          B=B, heads=attn.heads, n_q=n, softmax_scale=SOFTMAX_SCALE, tc=rt.tc)
+                          B=B, heads=attn.heads, n_q=n, softmax_scale=SOFTMAX_SCALE, tc=rt.tc, scratch_owner=id(rt))
         out = attn.project_out(o, M, residual)
         return out.view(B, n, C)
 

@@ -42,6 +42,12 @@ struct alignas(64) AttnTcParams {
   int B, heads, n_q;
   float scale_log2;  // softmax_scale * log2(e)
   int wide_out;      // output rows start on 32-byte boundaries (256-bit stores in the attn_ts epilogue)
+  // attn_ts work partition: CTA c owns the (tile, key block) units [c * units_per_cta, (c + 1) * units_per_cta) of the
+  // tile-major unit list; a tile cut by a CTA boundary is finished by the last CTA to arrive on its ticket
+  int units_per_cta;
+  long long total_units;
+  float* ws_part;          // [grid][2][PART_FLOATS]: unnormalised O rows, reference max, row sum of a partial tile
+  unsigned int* ws_ticket; // [tiles], zero between launches
 };
 
 constexpr int ATT_TMEM_COLS = 256;  // S (128) + 2 x O (64): two CTAs share the SM's 512 columns
@@ -315,6 +321,47 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
 // freed space, and no local-memory spills in the exp loop.
 constexpr int ATS_THREADS = 256;
 constexpr int ATS_KV_STAGES = 3;
+constexpr int ATS_PART_FLOATS = 128 * 64 + 256;  // one parked partial tile: O [128][64], m_ref [128], l [128]
+constexpr int ATS_MAX_PARTS = 8;                 // a tile is cut into at most this many parts
+
+// Work list of one attn_ts CTA.  Two partitions of the (tile, key block) units:
+//   whole tiles, round robin (units_per_cta == 0): CTA c takes tiles c, c + grid, ...;
+//   contiguous unit ranges (units_per_cta = L > 0): CTA c takes units [c * L, (c + 1) * L) of the tile-major list, so a
+//   tile may be cut at a key-block boundary (SEGMENTS of one tile in neighbouring CTAs, merged by the last to arrive).
+struct AtsSegments {
+  long long u, u_end;
+  int nb, tile_step, total_tiles, L;
+  int tile, j0, j1;     // current segment: key blocks [j0, j1) of `tile`
+  bool opens_range;     // the segment starts at the first unit of this CTA's range
+  __device__ __forceinline__ AtsSegments(const AttnTcParams& p, int nb_, int total_tiles_)
+      : nb(nb_), tile_step(gridDim.x), total_tiles(total_tiles_), L(p.units_per_cta) {
+    if (L > 0) {
+      u = static_cast<long long>(blockIdx.x) * L;
+      u_end = u + L < p.total_units ? u + L : p.total_units;
+    } else {
+      u = blockIdx.x;  // tile index
+      u_end = total_tiles_;
+    }
+    tile = j0 = j1 = 0;
+    opens_range = false;
+  }
+  __device__ __forceinline__ bool next() {
+    if (u >= u_end) return false;
+    if (L > 0) {
+      tile = static_cast<int>(u / nb);
+      j0 = static_cast<int>(u - static_cast<long long>(tile) * nb);
+      j1 = static_cast<long long>(nb - j0) < u_end - u ? nb : j0 + static_cast<int>(u_end - u);
+      opens_range = (u == static_cast<long long>(blockIdx.x) * L);
+      u += j1 - j0;
+    } else {
+      tile = static_cast<int>(u);
+      j0 = 0;
+      j1 = nb;
+      u += tile_step;
+    }
+    return true;
+  }
+};
 
 // PERBLOCK = true: every key segment fits ONE 128-key block (the decoupled text + image cross-attention: 77 and
 // 64 keys).  Block j is segment j with its own K/V tensors; its softmax is complete after that block, so P is
@@ -343,15 +390,21 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
   uint64_t* s_empty = s_full + 1;                      // 1
   uint64_t* p_full = s_empty + 1;                      // 2: P columns [0,32) / [32,64) written
   uint64_t* p_empty = p_full + 2;                      // 2: the MMAs reading that half of P retired
-  uint64_t* q_empty = p_empty + 2;                     // 1: the Q K^T MMAs of a tile retired, sQ may be refilled
+  uint64_t* q_empty = p_empty + 2;                     // 1: the Q K^T MMAs of a segment retired, sQ may be refilled
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
+  volatile unsigned int* s_ticket = reinterpret_cast<volatile unsigned int*>(tmem_slot + 1);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   pdl_trigger();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // persistent: CTA c walks tiles c, c + grid, ... (tile = (batch, head, 128-query block), query block fastest so
-  // that co-running CTAs share one head's K/V in L2); barriers, TMEM and the K/V ring live across tiles, and the
-  // producer runs ahead into the next tile while the softmax of the current one finishes
+  // persistent: the (tile, key block) units — tile = (batch, head, 128-query block), query block fastest so that
+  // co-running CTAs share one head's K/V in L2 — are listed tile-major and CTA c owns the contiguous range
+  // [c * L, (c + 1) * L).  With 320 tiles of 8 blocks on 296 resident CTAs a tile-granular walk needs two waves (the
+  // second one 8 % full); the unit-granular ranges give every CTA 8.65 blocks.  A range is processed as SEGMENTS
+  // (tile, first block, last block); a segment that covers only part of its tile leaves (O, m, l) in a workspace slot and
+  // takes a ticket on the tile: whoever arrives last merges the parts IN CTA ORDER (bit-deterministic) and writes the
+  // tile's output.  Barriers, TMEM and the K/V ring live across segments, and the producer runs ahead into the next
+  // segment while the softmax of the current one finishes.
   const int nqt = (p.n_q + 127) >> 7;
   const int total_tiles = nqt * p.heads * p.B;
   const int nb = PERBLOCK ? p.n_seg : p.nblk[0];
@@ -397,22 +450,23 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       int st = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (AtsSegments sg(p, nb, total_tiles); sg.next(); ++it) {
+        const int tile = sg.tile, j0 = sg.j0, j1 = sg.j1;
         const int qt = tile % nqt, hb = tile / nqt;
         const int h = hb % p.heads, b = hb / p.heads, q0 = qt * 128;
-        if (it > 0) mbar_wait_sleep(q_empty, (it - 1) & 1, 20000);  // Q K^T of the previous tile has read sQ
+        if (it > 0) mbar_wait_sleep(q_empty, (it - 1) & 1, 20000);  // Q K^T of the previous segment has read sQ
         if (elect_one()) {
           mbar_expect_tx(q_full, TILE_BYTES);
           tma_load_3d(sQ, &p.tmQ, q_full, p.q_off + h * 64, q0, b);
         }
         __syncwarp();
-        for (int jb = 0; jb < nb; ++jb) {
+        for (int jb = j0; jb < j1; ++jb) {
           mbar_wait_sleep(&kv_empty[st], ph ^ 1, 20000);
           if (elect_one()) {
             mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-            const int sg = PERBLOCK ? jb : 0, jr = PERBLOCK ? 0 : jb * 128;
-            tma_load_3d(sK + st * TILE_BYTES, &p.tmK[sg], &kv_full[st], p.k_off[sg] + h * 64, jr, b);
-            tma_load_3d(sV + st * TILE_BYTES, &p.tmV[sg], &kv_full[st], p.v_off[sg] + h * 64, jr, b);
+            const int ks = PERBLOCK ? jb : 0, jr = PERBLOCK ? 0 : jb * 128;
+            tma_load_3d(sK + st * TILE_BYTES, &p.tmK[ks], &kv_full[st], p.k_off[ks] + h * 64, jr, b);
+            tma_load_3d(sV + st * TILE_BYTES, &p.tmV[ks], &kv_full[st], p.v_off[ks] + h * 64, jr, b);
           }
           __syncwarp();
           if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
@@ -444,9 +498,10 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       int st = 0, st_prev = 0;
       uint32_t ph = 0, g = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (AtsSegments sg(p, nb, total_tiles); sg.next(); ++it) {
+        const int nbs = sg.j1 - sg.j0;  // blocks of this segment; jb below counts from the segment's first block
         mbar_wait_sleep(q_full, it & 1, 2000);
-        for (int jb = 0; jb < nb; ++jb, ++g) {
+        for (int jb = 0; jb < nbs; ++jb, ++g) {
           mbar_wait_sleep(&kv_full[st], ph, 2000);
           mbar_wait_sleep(s_empty, (g & 1) ^ 1, 2000);
           tc_fence_after();
@@ -456,7 +511,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_S, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
             umma_commit(s_full);
-            if (jb == nb - 1) umma_commit(q_empty);  // last read of this tile's Q
+            if (jb == nbs - 1) umma_commit(q_empty);  // last read of this segment's Q
           }
           __syncwarp();
           // P V of the previous block; the first P V of a tile overwrites O (accumulate = 0): the softmax warps
@@ -465,7 +520,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
           st_prev = st;
           if (++st == ATS_KV_STAGES) { st = 0; ph ^= 1; }
         }
-        issue_pv(g - 1, nb - 1, st_prev);
+        issue_pv(g - 1, nbs - 1, st_prev);
       }
     }
   } else {
@@ -477,16 +532,18 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
     const uint32_t trow = static_cast<uint32_t>(lane_base) << 16;
     const float sl2 = p.scale_log2;
     const float kLazy = 8.0f / sl2;  // advance the reference max only when exp2 arguments would exceed 8
-    uint32_t gb = 0;  // block counter over all tiles of this CTA: every per-block barrier completes once per block
+    uint32_t gb = 0;  // block counter over all segments of this CTA: every per-block barrier completes once per block
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (AtsSegments sg(p, nb, total_tiles); sg.next();) {
+    const int tile = sg.tile, j0 = sg.j0, j1 = sg.j1;
+    const bool seg_at_range_start = sg.opens_range;
     const int qt = tile % nqt, hb = tile / nqt;
     const int h = hb % p.heads, b = hb / p.heads, q0 = qt * 128;
     const int qi = q0 + row;
     bf16* optr = p.out + (static_cast<long long>(b) * p.n_q + qi) * p.ldo + p.out_off + h * 64;
     float m_ref = -INFINITY, l_run = 0.f;
 #pragma unroll 1
-    for (int jb = 0; jb < nb; ++jb, ++gb) {
+    for (int jb = j0; jb < j1; ++jb, ++gb) {
       const int valid = PERBLOCK ? min(128, p.kv_len[jb]) : min(128, p.kv_len[0] - jb * 128);
       mbar_wait_sleep(s_full, gb & 1, 20000);
       tc_fence_after();
@@ -509,15 +566,17 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         for (int j = 0; j < 128; ++j)
           if (j >= valid) sr[j] = 0xff800000u;  // -inf
       }
+      // row maximum with three-input max (FMNMX3): 8 independent chains of 8 instructions instead of 16
       float mxs[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mxs[c] = __uint_as_float(sr[c]);
+      for (int c = 0; c < 8; ++c) mxs[c] = fmax3(__uint_as_float(sr[c]), __uint_as_float(sr[8 + c]), __uint_as_float(sr[16 + c]));
 #pragma unroll
-      for (int j = 8; j < 128; j += 8)
+      for (int j = 24; j < 120; j += 16)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(sr[j + c]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+        for (int c = 0; c < 8; ++c) mxs[c] = fmax3(mxs[c], __uint_as_float(sr[j + c]), __uint_as_float(sr[j + 8 + c]));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(sr[120 + c]));
+      const float mx = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
       if (PERBLOCK) {
         // complete softmax of this segment in registers: e -> sum -> P = e * seg_scale / sum
         const float mneg = -mx * sl2;
@@ -552,32 +611,31 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         l_run = 1.0f;
         continue;
       }
-      const bool first = (jb == 0);
+      const bool first = (jb == j0);
       const bool grow = !first && (mx > m_ref + kLazy);
       const float m_old = m_ref;
       if (first || grow) m_ref = mx;
       const float mneg = -m_ref * sl2;
+      // 32 scores -> 16 packed probabilities: one SFU exp2 (or FMA-pipe polynomial) per element, fp32 row sums.
+      // (ex2.approx.f16x2 was tried for the fp16 build: ptxas lowers it to two scalar MUFU.EX2.F16 plus a repack — no
+      // packed SFU exponential exists on sm_100 — so it saves nothing.)
       float sums[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) sums[c] = 0.f;
+      auto exp32 = [&](const uint32_t* s32, uint32_t (&pk)[16]) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(s32[j]), sl2, mneg));
+          const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(s32[j + 1]), sl2, mneg));
+          sums[j & 7] += e0;
+          sums[(j + 1) & 7] += e1;
+          pk[j >> 1] = pack_bf16(e0, e1);
+        }
+      };
       // exps of the first 64 keys are computed BEFORE waiting for P V_{j-1}: its tail is hidden under them
       uint32_t pk0[16], pk1[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[j]), sl2, mneg));
-        const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[j + 1]), sl2, mneg));
-        sums[j & 7] += e0;
-        sums[(j + 1) & 7] += e1;
-        pk0[j >> 1] = pack_bf16(e0, e1);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[32 + j]), sl2, mneg));
-        const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[32 + j + 1]), sl2, mneg));
-        sums[j & 7] += e0;
-        sums[(j + 1) & 7] += e1;
-        pk1[j >> 1] = pack_bf16(e0, e1);
-      }
+      exp32(&sr[0], pk0);
+      exp32(&sr[32], pk1);
       if (__any_sync(0xffffffffu, grow)) {
         // rare: rescale O (TMEM) and l by exp2((m_old - mx) * sl2) for the rows that need it; O must be stable
         mbar_wait(&p_empty[1], (gb & 1) ^ 1);
@@ -605,14 +663,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
 #pragma unroll
       for (int g = 2; g < 4; ++g) {
         uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float e0 = exp2_sel<POLY>(j, fmaf(__uint_as_float(sr[g * 32 + j]), sl2, mneg));
-          const float e1 = exp2_sel<POLY>(j + 1, fmaf(__uint_as_float(sr[g * 32 + j + 1]), sl2, mneg));
-          sums[j & 7] += e0;
-          sums[(j + 1) & 7] += e1;
-          pk[j >> 1] = pack_bf16(e0, e1);
-        }
+        exp32(&sr[g * 32], pk);
         if (g == 2) {
           mbar_wait(&p_empty[1], (gb & 1) ^ 1);  // all of P V_{j-1} retired
           tc_fence_after();
@@ -624,9 +675,72 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       tc_fence_before();
       mbar_arrive(&p_full[1]);
     }
-    // all key blocks done: wait for the last P V, then O / l
+    // all key blocks of the segment done: wait for the last P V, then O / l
     mbar_wait(&p_empty[1], (gb - 1) & 1);
     tc_fence_after();
+    if (!PERBLOCK && (j0 != 0 || j1 != nb)) {
+      // ---- partial tile: park (O, m_ref, l) in this CTA's workspace slot (0: the segment opens the CTA's range, 1: it
+      // closes it), take a ticket on the tile; the last part to arrive merges all parts in CTA order
+      float* mine = p.ws_part + (static_cast<long long>(blockIdx.x) * 2 + (seg_at_range_start ? 0 : 1)) * ATS_PART_FLOATS;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(tmem_O + trow + half * 32, r);
+        tmem_ld_wait();
+        float* dst = mine + row * 64 + half * 32;
+#pragma unroll
+        for (int d = 0; d < 32; d += 8)
+          st_global_256(dst + d, r[d], r[d + 1], r[d + 2], r[d + 3], r[d + 4], r[d + 5], r[d + 6], r[d + 7]);
+      }
+      mine[128 * 64 + row] = m_ref;
+      mine[128 * 64 + 128 + row] = l_run;
+      tc_fence_before();
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long t_u0 = static_cast<long long>(tile) * nb;
+      const int c_first = static_cast<int>(t_u0 / p.units_per_cta);
+      const int c_last = static_cast<int>((t_u0 + nb - 1) / p.units_per_cta);
+      if (threadIdx.x == 0) *s_ticket = atomicAdd(&p.ws_ticket[tile], 1u);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool last = *s_ticket == static_cast<unsigned int>(c_last - c_first);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the ticket before a later segment overwrites it
+      if (last) {
+        __threadfence();
+        float acc[64];
+#pragma unroll
+        for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+        float m_all = -INFINITY, l_all = 0.f;
+#pragma unroll 1
+        for (int c = c_first; c <= c_last; ++c) {
+          // CTA c's segment on this tile starts at max(c * L, t_u0): it opens c's range (slot 0) iff c * L >= t_u0
+          const int slot = static_cast<long long>(c) * p.units_per_cta >= t_u0 ? 0 : 1;
+          const float* part = p.ws_part + (static_cast<long long>(c) * 2 + slot) * ATS_PART_FLOATS;
+          const float m_p = __ldcg(part + 128 * 64 + row), l_p = __ldcg(part + 128 * 64 + 128 + row);
+          const float m_new = fmaxf(m_all, m_p);
+          const float a_old = ex2_approx((m_all - m_new) * sl2), a_p = ex2_approx((m_p - m_new) * sl2);
+          l_all = l_all * a_old + l_p * a_p;
+          m_all = m_new;
+          const float4* src = reinterpret_cast<const float4*>(part + row * 64);
+#pragma unroll
+          for (int d4 = 0; d4 < 16; ++d4) {
+            const float4 v = __ldcg(src + d4);
+            acc[4 * d4] = acc[4 * d4] * a_old + v.x * a_p;
+            acc[4 * d4 + 1] = acc[4 * d4 + 1] * a_old + v.y * a_p;
+            acc[4 * d4 + 2] = acc[4 * d4 + 2] * a_old + v.z * a_p;
+            acc[4 * d4 + 3] = acc[4 * d4 + 3] * a_old + v.w * a_p;
+          }
+        }
+        if (threadIdx.x == 0) p.ws_ticket[tile] = 0u;  // self-resetting: the workspace is reusable by the next launch
+        if (qi < p.n_q) {
+          const float w = p.seg_scale[0] / l_all;
+#pragma unroll
+          for (int d = 0; d < 64; d += 8)
+            *reinterpret_cast<uint4*>(optr + d) = make_uint4(pack_bf16(acc[d] * w, acc[d + 1] * w), pack_bf16(acc[d + 2] * w, acc[d + 3] * w),
+                                                             pack_bf16(acc[d + 4] * w, acc[d + 5] * w), pack_bf16(acc[d + 6] * w, acc[d + 7] * w));
+        }
+      }
+      continue;
+    }
     const float w = PERBLOCK ? 1.0f : p.seg_scale[0] / l_run;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
@@ -660,7 +774,7 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
       }
     }
     tc_fence_before();
-    }  // tiles
+    }  // segments
   }
 
   tc_fence_before();
@@ -687,6 +801,13 @@ int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int B) {
 
 }  // namespace
 }  // namespace iir
+
+extern "C" int64_t iir_attn_workspace_bytes(int B, int heads, int n_q) {
+  // tickets (one per 128-query tile) + two parked partial tiles per resident CTA; see attn_ts_kernel
+  if (B <= 0 || heads <= 0 || n_q <= 0) return 0;
+  const long long tiles = static_cast<long long>((n_q + 127) / 128) * heads * B;
+  return 2LL * iir::sm_count() * 2 * iir::ATS_PART_FLOATS * 4 + tiles * 4;
+}
 
 extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   using namespace iir;
@@ -725,9 +846,50 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
 
   const size_t smem = 7 * TILE_BYTES + 256;
   dim3 grid((a->n_q + 127) / 128, a->heads, a->B);
-  // attn_ts kernels are persistent: two CTAs per SM walk the (batch, head, query block) tiles
+  // attn_ts kernels are persistent: up to two CTAs per SM, each owning a contiguous range of (tile, key block) units
+  const bool one_block_each = a->n_seg == 2 && a->kv_len[0] <= 128 && a->kv_len[1] <= 128;
   const long long ats_tiles = static_cast<long long>(grid.x) * grid.y * grid.z;
-  const dim3 ats_grid(static_cast<unsigned>(ats_tiles < 2LL * sm_count() ? ats_tiles : 2LL * sm_count()));
+  const int ats_nb = one_block_each ? a->n_seg : p.nblk[0];
+  const long long slots = 2LL * sm_count();
+  p.total_units = ats_tiles * ats_nb;
+  static int split_env = -1;
+  if (split_env < 0) {
+    const char* ev = getenv("IIR_ATTN_SPLIT");  // 0 = tile-granular ranges only (no partial tiles)
+    split_env = ev ? atoi(ev) : 1;
+  }
+  // IIR_ATTN_SPLIT: 0 = never cut tiles; 1 (default) = cut them when whole tiles dealt round robin would leave more than
+  // a quarter of the CTA slots idle AND a tile is long enough (>= 32 key blocks) for the balance to outweigh parking and
+  // merging the partial tiles (measured, profiles/attn_micro_r02.txt: 4096 tokens x 10 heads, one CFG branch: 87 -> 79 us;
+  // 1024 tokens, 8 blocks per tile: 31 -> 40 us); 2 = whenever the unit ranges do not fall on tile boundaries
+  const long long rr_waves = (ats_tiles + slots - 1) / slots;
+  const bool rr_unbalanced = 4 * ats_tiles < 3 * slots * rr_waves;  // round robin keeps < 75 % of the CTA slots busy
+  bool split = split_env && a->n_seg == 1 && a->workspace != nullptr && (split_env == 2 || (ats_nb >= 32 && rr_unbalanced));
+  long long L = 0;
+  if (split) {
+    L = (p.total_units + slots - 1) / slots;
+    const long long min_len = (ats_nb + ATS_MAX_PARTS - 2) / (ATS_MAX_PARTS - 1);  // at most ATS_MAX_PARTS parts per tile
+    if (L < min_len) L = min_len;
+    if (L % ats_nb == 0) split = false;  // the ranges would fall on tile boundaries anyway
+  }
+  long long ats_ctas;
+  if (split) {
+    ats_ctas = (p.total_units + L - 1) / L;
+    p.units_per_cta = static_cast<int>(L);
+    // layout: [2 * sm_count() CTAs][2 slots][ATS_PART_FLOATS] partial tiles at a FIXED offset, then one ticket word per
+    // tile — launches of different shapes share the workspace, so the (always-zero-between-launches) tickets must never
+    // overlap another launch's partial-tile area
+    const long long part_bytes = slots * 2 * ATS_PART_FLOATS * 4;
+    const long long need = part_bytes + ats_tiles * 4;
+    IIR_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0 && a->workspace_bytes >= need,
+                "iir_attn_tc: workspace of %lld bytes (256-byte aligned, zero-initialised) needed, got %lld",
+                need, (long long)a->workspace_bytes);
+    p.ws_part = reinterpret_cast<float*>(a->workspace);
+    p.ws_ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(a->workspace) + part_bytes);
+  } else {
+    ats_ctas = ats_tiles < slots ? ats_tiles : slots;  // whole tiles, round robin
+    p.units_per_cta = 0;
+  }
+  const dim3 ats_grid(static_cast<unsigned>(ats_ctas));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   static int v1 = -1;
@@ -735,7 +897,6 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
     const char* ev = getenv("IIR_ATTN_V1");
     v1 = (ev && ev[0] == '1') ? 1 : 0;
   }
-  const bool one_block_each = a->n_seg == 2 && a->kv_len[0] <= 128 && a->kv_len[1] <= 128;
   static int poly = -1;
   if (poly < 0) {
     const char* ev = getenv("IIR_ATTN_POLY");  // 0 = all exponentials on the SFU; n = every n-th on the FMA pipe

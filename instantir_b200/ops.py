@@ -235,13 +235,34 @@ def conv3x3_direct(x, w, bias, out, *, in_nchw: bool, out_nchw: bool, n_img: int
     return out
 
 
+_ATTN_WS = {}
+
+
+def _attn_workspace(lib, device, B: int, heads: int, n_q: int, owner=None) -> torch.Tensor:
+    """Zero-initialised scratch of the self-attention kernel (partial tiles + tickets; every launch leaves the tickets
+    zero, launches are stream-ordered, so one buffer per (device, owner) serves every attention of a model).  `owner`
+    separates models that may run CONCURRENTLY on different streams (UNet down path || Aggregator)."""
+    need = int(lib.iir_attn_workspace_bytes(B, heads, n_q))
+    key = (torch.device(device).index, owner)
+    bufs = _ATTN_WS.setdefault(key, [])
+    if not bufs or bufs[-1].numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.IIRError("attention workspace must be created before CUDA-graph capture: run the op once eagerly first")
+        # outgrown buffers stay alive: CUDA graphs captured earlier hold their addresses
+        bufs.append(torch.zeros(max(need, 32 << 20), dtype=torch.uint8, device=device))
+    return bufs[-1]
+
+
 def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Sequence[int],
               ldks: Sequence[int], vs: Sequence[torch.Tensor], v_offs: Sequence[int],
               ldvs: Sequence[int], kv_lens: Sequence[int], seg_scales: Sequence[float], out,
               out_off: int, ldo: int, *, B: int, heads: int, n_q: int, softmax_scale: float,
-              tc: bool = True):
+              tc: bool = True, scratch_owner=None):
     lib = _L(q, out)
     a = _lib.AttnArgs()
+    if tc and len(ks) == 1:
+        ws = _attn_workspace(lib, q.device, B, heads, n_q, scratch_owner)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.q, a.ldq, a.q_off = _p(q), ldq, q_off
     a.n_seg = len(ks)
     for s in range(len(ks)):

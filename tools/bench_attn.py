@@ -7,9 +7,11 @@ import torch.nn.functional as F
 from instantir_b200 import ops
 torch.set_grad_enabled(False)
 dev = "cuda"
+H16 = H16 if os.environ.get("IIR_TEST_H16", "fp16") == "bf16" else torch.float16
 only = sys.argv[1] if len(sys.argv) > 1 else None
 # (B, heads, n_q, kv_lens)
 shapes = [(2, 20, 1024, [1024]), (2, 20, 2048, [2048]), (2, 10, 4096, [4096]), (2, 10, 8192, [8192]),
+          (1, 20, 1024, [1024]), (1, 10, 4096, [4096]), (2, 10, 16384, [16384]),
           (2, 20, 1024, [77, 64]), (2, 10, 4096, [77, 64])]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -33,10 +35,10 @@ for B, heads, n, kvs in shapes:
     if only and str(n) != only:
         continue
     C = heads * 64
-    q = torch.randn(B, n, C, device=dev, dtype=torch.bfloat16)
-    ks = [torch.randn(B, m, C, device=dev, dtype=torch.bfloat16) for m in kvs]
-    vs = [torch.randn(B, m, C, device=dev, dtype=torch.bfloat16) for m in kvs]
-    out = torch.empty(B, n, C, device=dev, dtype=torch.bfloat16)
+    q = torch.randn(B, n, C, device=dev, dtype=H16)
+    ks = [torch.randn(B, m, C, device=dev, dtype=H16) for m in kvs]
+    vs = [torch.randn(B, m, C, device=dev, dtype=H16) for m in kvs]
+    out = torch.empty(B, n, C, device=dev, dtype=H16)
     fl = 4.0 * B * heads * n * sum(kvs) * 64
     t = timeit(lambda: ops.attention(q, 0, C, ks, [0] * len(kvs), [C] * len(kvs), vs, [0] * len(kvs), [C] * len(kvs), kvs,
                                      [1.0] * len(kvs), out, 0, C, B=B, heads=heads, n_q=n, softmax_scale=0.125))

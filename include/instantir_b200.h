@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 9
+#define IIR_ABI_VERSION 10
 
 typedef enum {
   IIR_OK = 0,
@@ -37,7 +37,8 @@ typedef enum {
  * libinstantir_b200_fp16.so (-DIIR_FP16) = IEEE fp16, the reference's own inference precision
  * (infer.py:119).  iir_h16_dtype() tells which; the other 16-bit code is rejected with IIR_ERR_INVALID. */
 typedef enum { IIR_F32 = 0, IIR_BF16 = 1, IIR_F16 = 2 } iir_dtype;
-typedef enum { IIR_ACT_NONE = 0, IIR_ACT_SILU = 1, IIR_ACT_GELU = 2 } iir_act;
+/* QUICK_GELU = x * sigmoid(1.702 x): the activation of CLIP-L's MLP (transformers CLIPMLP, hidden_act "quick_gelu") */
+typedef enum { IIR_ACT_NONE = 0, IIR_ACT_SILU = 1, IIR_ACT_GELU = 2, IIR_ACT_QUICK_GELU = 3 } iir_act;
 /* paired epilogues: weight rows are packed per `bn`-wide tile as [first half | second half]
  *   GEGLU: out = (x1 + b1) * gelu_erf(x2 + b2)      reference module/min_sdxl.py:502-510
  *   SFT  : out = h * (gamma + 1) + beta             reference module/aggregator.py:70-90   */
@@ -143,6 +144,9 @@ typedef struct {
    * iir_attn_workspace_bytes(B, heads, n_q) bytes, 256-byte aligned, ZERO before the first use (every launch leaves its
    * ticket words zero again); launches that may run concurrently need distinct workspaces.  NULL = whole tiles per CTA. */
   void* workspace; int64_t workspace_bytes;
+  /* 1 = causal self-attention (one segment, n_q == kv_len): query i attends keys 0..i — the CLIP text encoders
+   * (pipelines/sdxl_instantir.py:522,580 call transformers' CLIPTextModel, whose encoder applies a causal mask)          */
+  int causal;
 } iir_attn_args;
 
 int64_t iir_attn_workspace_bytes(int B, int heads, int n_q);
@@ -217,6 +221,21 @@ int iir_add(const void* a, int a_dtype, const void* b, int b_dtype, void* out, i
 
 /* out = alpha * x  (Aggregator.forward's `conditioning_scale`, module/aggregator.py:963-964)       */
 int iir_scale(const void* x, int x_dtype, void* out, int out_dtype, int64_t n, float alpha, void* stream);
+
+/* ---- once-per-image encoders: transformers' CLIPTextModel(WithProjection) and Dinov2Model as called at
+ * pipelines/sdxl_instantir.py:522,580,643-667 ---------------------------------------------------------------------- */
+/* CLIPTextEmbeddings: out[r, :] = token_embedding[ids[r], :] + position_embedding[r % seq_len, :]; fp32 tables [*, dim],
+ * out fp32 [n_tokens, dim] (the residual stream of the text encoder)                                                */
+int iir_embed_tokens(const int64_t* ids, int n_tokens, int seq_len, const float* token_embedding, int vocab,
+                     const float* position_embedding, int dim, float* out, void* stream);
+/* Dinov2PatchEmbeddings as a GEMM operand: NCHW fp32 image [n_img, C, H, W] -> rows of non-overlapping patch x patch
+ * windows [n_img * (H/patch) * (W/patch), ld_out] in (c, ky, kx) order (= Conv2d weight flattening), columns past
+ * C*patch*patch zero-filled (ld_out = that width rounded up to a multiple of 8)                                     */
+int iir_patchify(const float* img, int n_img, int C, int H, int W, int patch, void* out, int out_dtype, int ld_out,
+                 void* stream);
+/* Dinov2Embeddings: out[b, 0, :] = cls + pos[0]; out[b, 1 + p, :] = patches[b * P + p, :] + pos[1 + p]; all fp32      */
+int iir_vit_assemble(const float* patches, const float* cls, const float* pos, float* out, int n_img, int P, int dim,
+                     void* stream);
 
 /* sinusoidal timestep embedding [cos|sin], flip_sin_to_cos=True, freq_shift=0
  * (module/min_sdxl.py:205-224): t [n] fp32 -> out [n, dim]                                  */

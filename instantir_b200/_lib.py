@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 F32, BF16, F16 = 0, 1, 2
 # 16-bit operand type of the default library build: IEEE fp16 is the reference's own inference precision
 # (infer.py:119) and the one that meets the north star's <= 1e-2 per-step latent bar; the bf16
 # build stays available as precision="bf16"
 DEFAULT_H16 = F16
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3
 PAIR_NONE, PAIR_GEGLU, PAIR_SFT = 0, 1, 2
 
 # every symbol include/instantir_b200.h declares (tests/test_abi.py checks the two lists agree)
@@ -29,7 +29,7 @@ SYMBOLS = [
     "iir_attn_workspace_bytes", "iir_attn_tc", "iir_attn_simt",
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add", "iir_scale",
-    "iir_timestep_embedding", "iir_linear_small",
+    "iir_timestep_embedding", "iir_linear_small", "iir_embed_tokens", "iir_patchify", "iir_vit_assemble",
     "iir_step_prologue", "iir_lcm_step", "iir_cfg_ddpm_step", "iir_cfg_rescale", "iir_add_noise", "iir_gaussian_sample",
 ]
 
@@ -73,6 +73,7 @@ class AttnArgs(C.Structure):
         ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int),
         ("softmax_scale", C.c_float),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("causal", C.c_int),
     ]
 
 
@@ -113,6 +114,9 @@ def _declare(lib):
     lib.iir_step_prologue.argtypes = [vp, i64, i, vp, f, vp, f, vp, i, vp]
     lib.iir_timestep_embedding.argtypes = [vp, i, i, vp, i, vp]
     lib.iir_linear_small.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, vp]
+    lib.iir_embed_tokens.argtypes = [vp, i, i, vp, i, vp, i, vp, vp]
+    lib.iir_patchify.argtypes = [vp, i, i, i, i, i, vp, i, i, vp]
+    lib.iir_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]
     lib.iir_cfg_rescale.argtypes = [vp, vp, vp, i64, i64, f, f, vp]
     lib.iir_gaussian_sample.argtypes = [vp, vp, vp, i64, i64, f, vp]
     lib.iir_lcm_step.argtypes = [vp, i, vp, vp, i64, f, f, f, vp]

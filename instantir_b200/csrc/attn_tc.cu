@@ -44,6 +44,7 @@ struct alignas(64) AttnTcParams {
   int wide_out;      // output rows start on 32-byte boundaries (256-bit stores in the attn_ts epilogue)
   // attn_ts work partition: CTA c owns the (tile, key block) units [c * units_per_cta, (c + 1) * units_per_cta) of the
   // tile-major unit list; a tile cut by a CTA boundary is finished by the last CTA to arrive on its ticket
+  int causal;  // query i attends keys 0..i (one segment, n_q == kv_len)
   int units_per_cta;
   long long total_units;
   float* ws_part;          // [grid][2][PART_FLOATS]: unnormalised O rows, reference max, row sum of a partial tile
@@ -566,6 +567,12 @@ attn_ts_kernel(const __grid_constant__ AttnTcParams p) {
         for (int j = 0; j < 128; ++j)
           if (j >= valid) sr[j] = 0xff800000u;  // -inf
       }
+      if (!PERBLOCK && p.causal && jb * 128 + 127 > qi) {  // causal mask: keys past this row's own position
+        const int lim = qi - jb * 128;  // last visible key of this block (may be negative: nothing visible)
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
+          if (j > lim) sr[j] = 0xff800000u;
+      }
       // row maximum with three-input max (FMNMX3): 8 independent chains of 8 instructions instead of 16
       float mxs[8];
 #pragma unroll
@@ -842,6 +849,8 @@ extern "C" int iir_attn_tc(const iir_attn_args* a, void* stream) {
   p.out_off = a->out_off;
   p.B = a->B; p.heads = a->heads; p.n_q = a->n_q;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+  IIR_REQUIRE(!a->causal || (a->n_seg == 1 && a->kv_len[0] == a->n_q), "iir_attn_tc: causal needs one segment with kv_len == n_q");
+  p.causal = a->causal;
   p.wide_out = (reinterpret_cast<uintptr_t>(a->out) % 32 == 0) && (a->ldo * 2) % 32 == 0 && (a->out_off * 2) % 32 == 0;
 
   const size_t smem = 7 * TILE_BYTES + 256;

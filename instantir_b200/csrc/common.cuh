@@ -195,6 +195,9 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 // same with the approximate divide (2 ulp): the IEEE divide above costs ~4x the instructions, which made
 // the GroupNorm+SiLU pass issue-bound instead of memory-bound
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x * sigmoid(1.702 x) (transformers QuickGELUActivation: CLIP-L's MLP)
+__device__ __forceinline__ float quick_gelu_f(float v) { return v / (1.0f + __expf(-1.702f * v)); }
+__device__ __forceinline__ float quick_gelu_fast(float v) { return __fdividef(v, 1.0f + __expf(-1.702f * v)); }
 // exact (erf) GELU, as torch.nn.functional.gelu default (module/min_sdxl.py:510)
 __device__ __forceinline__ float gelu_erf_f(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));

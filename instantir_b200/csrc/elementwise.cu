@@ -123,6 +123,55 @@ scale_kernel(const void* x, int x_bf, void* out, int out_bf, long long n, float 
     st1_any(out, out_bf, i, alpha * ld1_any(x, x_bf, i));
 }
 
+// CLIPTextEmbeddings (transformers modeling_clip.py): token + position embedding lookup, fp32
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const long long* __restrict__ ids, int n_tokens, int seq_len, const float* __restrict__ tok, int vocab,
+                    const float* __restrict__ pos, int dim, float* __restrict__ out) {
+  const int dv = dim >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < static_cast<long long>(n_tokens) * dv; i += gridDim.x * 256LL) {
+    const int r = static_cast<int>(i / dv), c = static_cast<int>(i - static_cast<long long>(r) * dv) * 4;
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float4 a = ld4(tok + id * dim + c), b = ld4(pos + static_cast<long long>(r % seq_len) * dim + c);
+    st4(out + static_cast<long long>(r) * dim + c, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+  }
+}
+
+// Dinov2PatchEmbeddings' Conv2d(C, D, patch, stride = patch) as a GEMM: one output row per patch, (c, ky, kx) order
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, int n_img, int C, int H, int W, int patch, void* out, int out_bf, int ld_out) {
+  const int gh = H / patch, gw = W / patch;
+  const long long total = static_cast<long long>(n_img) * gh * gw * ld_out;
+  const int kk = C * patch * patch;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int col = static_cast<int>(i % ld_out);
+    const long long row = i / ld_out;
+    float v = 0.f;
+    if (col < kk) {
+      const int c = col / (patch * patch), r2 = col - c * patch * patch, ky = r2 / patch, kx = r2 - ky * patch;
+      const int px = static_cast<int>(row % gw), py = static_cast<int>((row / gw) % gh), n = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+      v = img[((static_cast<long long>(n) * C + c) * H + py * patch + ky) * W + px * patch + kx];
+    }
+    st1_any(out, out_bf, i, v);
+  }
+}
+
+// Dinov2Embeddings: [cls | patch embeddings] + (interpolated) position embeddings
+__global__ void __launch_bounds__(256)
+vit_assemble_kernel(const float* __restrict__ patches, const float* __restrict__ cls, const float* __restrict__ pos,
+                    float* __restrict__ out, int n_img, int P, int dim) {
+  const int dv = dim >> 2;
+  const long long total = static_cast<long long>(n_img) * (P + 1) * dv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int c = static_cast<int>(i % dv) * 4;
+    const long long r = i / dv;
+    const int t = static_cast<int>(r % (P + 1)), b = static_cast<int>(r / (P + 1));
+    const float4 a = t == 0 ? ld4(cls + c) : ld4(patches + (static_cast<long long>(b) * P + t - 1) * dim + c);
+    const float4 q = ld4(pos + static_cast<long long>(t) * dim + c);
+    st4(out + r * dim + c, make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w));
+  }
+}
+
 // [cos | sin] of t * exp(-ln(10000) * k / half), fp32 like the reference (min_sdxl.py:205-224)
 __global__ void timestep_embedding_kernel(const float* t, int n, int dim, void* out, int out_bf) {
   const int half = dim >> 1;
@@ -229,6 +278,38 @@ extern "C" int iir_scale(const void* x, int x_dtype, void* out, int out_dtype, i
   scale_kernel<<<grid_for(n), 256, 0, st>>>(x, x_dtype == IIR_H16, out, out_dtype == IIR_H16, n, alpha);
   count_launch();
   return check_launch("iir_scale");
+}
+
+extern "C" int iir_embed_tokens(const int64_t* ids, int n_tokens, int seq_len, const float* token_embedding, int vocab,
+                                const float* position_embedding, int dim, float* out, void* stream) {
+  IIR_REQUIRE(ids && token_embedding && position_embedding && out && n_tokens > 0 && seq_len > 0 && vocab > 0 && dim > 0 && dim % 4 == 0,
+              "iir_embed_tokens: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  embed_tokens_kernel<<<grid_for(static_cast<long long>(n_tokens) * (dim / 4)), 256, 0, st>>>(
+      reinterpret_cast<const long long*>(ids), n_tokens, seq_len, token_embedding, vocab, position_embedding, dim, out);
+  count_launch();
+  return check_launch("iir_embed_tokens");
+}
+
+extern "C" int iir_patchify(const float* img, int n_img, int C, int H, int W, int patch, void* out, int out_dtype, int ld_out,
+                            void* stream) {
+  IIR_REQUIRE(img && out && n_img > 0 && C > 0 && patch > 0 && H > 0 && W > 0 && H % patch == 0 && W % patch == 0,
+              "iir_patchify: H=%d, W=%d must be multiples of patch=%d", H, W, patch);
+  IIR_REQUIRE(ld_out >= C * patch * patch && dtype_ok(out_dtype), "iir_patchify: ld_out too small or unsupported dtype");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  patchify_kernel<<<grid_for(static_cast<long long>(n_img) * (H / patch) * (W / patch) * ld_out), 256, 0, st>>>(
+      img, n_img, C, H, W, patch, out, out_dtype == IIR_H16, ld_out);
+  count_launch();
+  return check_launch("iir_patchify");
+}
+
+extern "C" int iir_vit_assemble(const float* patches, const float* cls, const float* pos, float* out, int n_img, int P, int dim,
+                                void* stream) {
+  IIR_REQUIRE(patches && cls && pos && out && n_img > 0 && P > 0 && dim > 0 && dim % 4 == 0, "iir_vit_assemble: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  vit_assemble_kernel<<<grid_for(static_cast<long long>(n_img) * (P + 1) * (dim / 4)), 256, 0, st>>>(patches, cls, pos, out, n_img, P, dim);
+  count_launch();
+  return check_launch("iir_vit_assemble");
 }
 
 extern "C" int iir_timestep_embedding(const float* t, int n, int dim, void* out, int out_dtype,

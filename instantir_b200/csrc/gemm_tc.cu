@@ -429,6 +429,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         } else if (p.act == IIR_ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        } else if (p.act == IIR_ACT_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = quick_gelu_fast(v[j]);
         }
         if (PAIR) {
           float g[32];

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) 
       if (p.rowvec) v += p.rowvec[static_cast<long long>(sample) * p.ld_rowvec + pn];
       if (p.act == IIR_ACT_SILU) v = silu_f(v);
       else if (p.act == IIR_ACT_GELU) v = gelu_erf_f(v);
+      else if (p.act == IIR_ACT_QUICK_GELU) v = quick_gelu_f(v);
       if (PAIR) {
         float g = acc2[i][j];
         if (p.bias) g += p.bias[pn2];
@@ -363,6 +364,7 @@ struct AttnSimtParams {
   void* out; long long ldo; int out_off;
   int B, heads, n_q;
   float scale;
+  int causal;
 };
 
 template <typename T>
@@ -384,7 +386,8 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnSimtParams p) 
     const T* V = reinterpret_cast<const T*>(p.v[s]) +
                  static_cast<long long>(b) * p.kv_len[s] * p.ldv[s] + p.v_off[s] + h * 64;
     float mx = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < p.kv_len[s]; ++j) {
+    const int n_keys = p.causal ? min(p.kv_len[s], i + 1) : p.kv_len[s];
+    for (int j = 0; j < n_keys; ++j) {
       const T* kr = K + static_cast<long long>(j) * p.ldk[s];
       float d = q0 * ld_f(kr + lane * 2) + q1 * ld_f(kr + lane * 2 + 1);
 #pragma unroll
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
         if (bias) v += bias[n];
         if (act == IIR_ACT_SILU) v = silu_f(v);
         else if (act == IIR_ACT_GELU) v = gelu_erf_f(v);
+        else if (act == IIR_ACT_QUICK_GELU) v = quick_gelu_f(v);
         st_f(out + static_cast<long long>(m) * N + n, v);
       }
     }
@@ -587,6 +591,8 @@ extern "C" int iir_attn_simt(const iir_attn_args* a, void* stream) {
   }
   p.out = a->out; p.ldo = a->ldo; p.out_off = a->out_off;
   p.B = a->B; p.heads = a->heads; p.n_q = a->n_q; p.scale = a->softmax_scale;
+  IIR_REQUIRE(!a->causal || (a->n_seg == 1 && a->kv_len[0] == a->n_q), "iir_attn_simt: causal needs one segment with kv_len == n_q");
+  p.causal = a->causal;
   long long rows = static_cast<long long>(a->B) * a->heads * a->n_q;
   int blocks = static_cast<int>((rows + 7) / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

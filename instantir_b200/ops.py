@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, BF16, F16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, BF16, F16, F32, PAIR_GEGLU, PAIR_NONE, PAIR_SFT  # noqa: F401
 
 
 # ---- optional per-launch profiling (bench.py's roofline leg): when PROFILE is a list every op
@@ -257,9 +257,10 @@ def attention(q, q_off: int, ldq: int, ks: Sequence[torch.Tensor], k_offs: Seque
               ldks: Sequence[int], vs: Sequence[torch.Tensor], v_offs: Sequence[int],
               ldvs: Sequence[int], kv_lens: Sequence[int], seg_scales: Sequence[float], out,
               out_off: int, ldo: int, *, B: int, heads: int, n_q: int, softmax_scale: float,
-              tc: bool = True, scratch_owner=None):
+              tc: bool = True, scratch_owner=None, causal: bool = False):
     lib = _L(q, out)
     a = _lib.AttnArgs()
+    a.causal = int(causal)
     if tc and len(ks) == 1:
         ws = _attn_workspace(lib, q.device, B, heads, n_q, scratch_owner)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -410,6 +411,36 @@ def step_prologue(latents, x_in, n_rep: int, *, t: float, t_dev, cond_scale: flo
                                      _p(cond_scale_dev), 0 if cond_scale_dev is None else cond_scale_dev.numel(), _stream()),
                "iir_step_prologue", lib)
     return x_in
+
+
+def embed_tokens(ids, token_embedding, position_embedding, out, *, seq_len: int):
+    """out[r] = token_embedding[ids[r]] + position_embedding[r % seq_len] (fp32 tables, fp32 out [n_tokens, dim])"""
+    lib = _L()
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise TypeError("embed_tokens: ids must be a contiguous int64 tensor")
+    _f32c(token_embedding, "token_embedding"), _f32c(position_embedding, "position_embedding"), _f32c(out, "out")
+    vocab, dim = token_embedding.shape
+    _lib.check(lib.iir_embed_tokens(_p(ids), ids.numel(), seq_len, _p(token_embedding), vocab, _p(position_embedding), dim, _p(out),
+                                    _stream()), "iir_embed_tokens", lib)
+    return out
+
+
+def patchify(img, out, *, patch: int):
+    """NCHW fp32 image -> [n_img * gh * gw, ld] rows of patch x patch windows in (c, ky, kx) order, zero-padded columns"""
+    lib = _L(out)
+    _f32c(img, "img")
+    n, c, h, w = img.shape
+    _lib.check(lib.iir_patchify(_p(img), n, c, h, w, patch, _p(out), _dt(out), out.stride(0), _stream()), "iir_patchify", lib)
+    return out
+
+
+def vit_assemble(patches, cls, pos, out, *, n_img: int, P: int):
+    """out[b, 0] = cls + pos[0]; out[b, 1 + p] = patches[b * P + p] + pos[1 + p]"""
+    lib = _L()
+    for t, n in ((patches, "patches"), (cls, "cls"), (pos, "pos"), (out, "out")):
+        _f32c(t, n)
+    _lib.check(lib.iir_vit_assemble(_p(patches), _p(cls), _p(pos), _p(out), n_img, P, patches.shape[-1], _stream()), "iir_vit_assemble", lib)
+    return out
 
 
 def timestep_embedding(t, dim: int, out):

@@ -4,11 +4,13 @@ the sm_100a kernels, with the reference's call surface for this path: ``guidance
 ``previewer_scheduler``, ``num_inference_steps``, ``generator``, ``timesteps``,
 ``controlnet_conditioning_scale``, ``init_latents_with_lq``, ``save_preview_row``...
 
-Scope: the per-timestep step, plus the VAE of row f1.  The once-per-image CLIP text and DINOv2
-encoders are "next" rows, so this pipeline takes their OUTPUTS: ``prompt_embeds`` / ``pooled_prompt_embeds``
-(and negatives) and ``ip_adapter_image_embeds`` (DINOv2 tokens).  ``image`` is a 4-channel LQ latent (the
-reference accepts latents there too, :1370-1382) or, when the pipeline was given ``vae=``, a 3-channel image in
-[-1, 1] that is encoded here; the result is latents (``output_type="latent"``) or decoded images ("pt" / "np").
+Scope: the per-timestep step, plus the "next" rows f1 (VAE) and f2 (CLIP text + DINOv2 encoders,
+instantir_b200/encoders.py).  Conditioning comes either as the encoders' OUTPUTS (``prompt_embeds`` /
+``pooled_prompt_embeds`` + negatives, ``ip_adapter_image_embeds``) or, when the pipeline was given the encoders, as
+``prompt`` / ``negative_prompt`` (strings through the user's tokenizers, or token-id tensors) and ``ip_adapter_image``
+(defaults to the LQ image, :1278-1279).  ``image`` is a 4-channel LQ latent (the reference accepts latents there too,
+:1370-1382) or, when the pipeline was given ``vae=``, a 3-channel image in [-1, 1] that is encoded here; the result
+is latents (``output_type="latent"``) or decoded images ("pt" / "np").
 
 What changes versus the reference's loop (same results, fewer launches):
   * which of the three step shapes runs at step i (previewer+aggregator+UNet / aggregator+UNet /
@@ -91,11 +93,108 @@ class InstantIRPipeline:
     _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]  # pipelines/sdxl_instantir.py:301
 
     def __init__(self, unet, aggregator, scheduler, vae=None, text_encoder=None, text_encoder_2=None, tokenizer=None,
-                 tokenizer_2=None, feature_extractor=None, image_encoder=None):
+                 tokenizer_2=None, feature_extractor=None, image_encoder=None, force_zeros_for_empty_prompt=True):
         self.unet, self.aggregator, self.scheduler = unet, aggregator, scheduler
-        self.vae, self.text_encoder, self.image_encoder = vae, text_encoder, image_encoder
+        self.vae, self.text_encoder, self.text_encoder_2, self.image_encoder = vae, text_encoder, text_encoder_2, image_encoder
+        self.tokenizer, self.tokenizer_2, self.feature_extractor = tokenizer, tokenizer_2, feature_extractor
+        self.config = SimpleNamespace(force_zeros_for_empty_prompt=force_zeros_for_empty_prompt)
         self.device = unet.rt.device
         self._graphs = {}
+        self._zero_image_embeds = {}
+
+    # ------------------------------------------------------------------- once-per-image encoders
+    def _token_ids(self, text, tokenizer, max_length=None):
+        """`text`: str / list of str (needs the HF-style tokenizer the pipeline was given) or an int64 tensor of ids"""
+        if torch.is_tensor(text):
+            return text.to(torch.int64)
+        if tokenizer is None:
+            raise ValueError("string prompts need `tokenizer` / `tokenizer_2` (HF CLIPTokenizer objects; tokenisation is host-side "
+                             "string processing), or pass token-id tensors / `prompt_embeds`")
+        return tokenizer(text, padding="max_length", max_length=max_length or tokenizer.model_max_length, truncation=True,
+                         return_tensors="pt").input_ids
+
+    def encode_prompt(self, prompt, prompt_2=None, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True,
+                      negative_prompt=None, negative_prompt_2=None, prompt_embeds=None, negative_prompt_embeds=None,
+                      pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        """pipelines/sdxl_instantir.py:400-632 on the sm_100a CLIP encoders (instantir_b200.encoders.CLIPTextModel): both
+        text encoders' penultimate hidden states concatenated along the feature axis ([B, 77, 768 + 1280]) and the pooled,
+        projected output of the second one; zeros for an absent negative prompt when force_zeros_for_empty_prompt."""
+        if isinstance(prompt, str):
+            prompt = [prompt]
+        batch_size = len(prompt) if prompt is not None else prompt_embeds.shape[0]
+        tokenizers = [self.tokenizer, self.tokenizer_2] if self.text_encoder is not None else [self.tokenizer_2]
+        encoders = [self.text_encoder, self.text_encoder_2] if self.text_encoder is not None else [self.text_encoder_2]
+        if prompt_embeds is None or (do_classifier_free_guidance and negative_prompt_embeds is None and negative_prompt is not None):
+            if self.text_encoder_2 is None:
+                raise ValueError("encoding prompts needs `text_encoder_2` (and usually `text_encoder`): "
+                                 "InstantIRPipeline(..., text_encoder=CLIPTextModel(...), text_encoder_2=CLIPTextModel(..., with_projection=True))")
+
+        def run(texts):
+            embeds, pooled = [], None
+            for text, tok, enc in zip(texts, tokenizers, encoders):
+                out = enc(self._token_ids(text, tok), output_hidden_states=True)
+                pooled = out[0]  # "we are only ALWAYS interested in the pooled output of the final text encoder" (:526)
+                embeds.append(out.hidden_states[-2] if clip_skip is None else out.hidden_states[-(clip_skip + 2)])
+            return torch.cat(embeds, dim=-1), pooled
+
+        if prompt_embeds is None:
+            prompt_2 = prompt if prompt_2 is None else prompt_2
+            prompt_2 = [prompt_2] if isinstance(prompt_2, str) else prompt_2
+            prompt_embeds, pooled_prompt_embeds = run([prompt, prompt_2][-len(encoders):])
+        zero_out = negative_prompt is None and self.config.force_zeros_for_empty_prompt
+        if do_classifier_free_guidance and negative_prompt_embeds is None and zero_out:
+            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+            negative_pooled_prompt_embeds = torch.zeros_like(pooled_prompt_embeds)
+        elif do_classifier_free_guidance and negative_prompt_embeds is None:
+            negative_prompt = negative_prompt if negative_prompt is not None else ""
+            negative_prompt_2 = negative_prompt_2 if negative_prompt_2 is not None else negative_prompt
+            neg = [batch_size * [n] if isinstance(n, str) else n for n in (negative_prompt, negative_prompt_2)]
+            if prompt is not None and not torch.is_tensor(prompt) and not torch.is_tensor(neg[0]) and type(prompt) is not type(neg[0]):
+                raise TypeError(f"`negative_prompt` should be the same type to `prompt`, but got {type(neg[0])} != {type(prompt)}.")
+            if batch_size != len(neg[0]):
+                raise ValueError(f"`negative_prompt` has batch size {len(neg[0])}, but `prompt` has batch size {batch_size}. Please make "
+                                 "sure that passed `negative_prompt` matches the batch size of `prompt`.")
+            negative_prompt_embeds, negative_pooled_prompt_embeds = run(neg[-len(encoders):])
+
+        def rep(t, pooled=False):
+            if t is None or num_images_per_prompt == 1:
+                return t
+            return t.repeat(1, num_images_per_prompt).view(t.shape[0] * num_images_per_prompt, -1) if pooled else \
+                t.repeat(1, num_images_per_prompt, 1).view(t.shape[0] * num_images_per_prompt, t.shape[1], -1)
+
+        return rep(prompt_embeds), rep(negative_prompt_embeds), rep(pooled_prompt_embeds, True), rep(negative_pooled_prompt_embeds, True)
+
+    def encode_image(self, image, device=None, num_images_per_prompt=1, output_hidden_states=None):
+        """pipelines/sdxl_instantir.py:635-669, DINO branch: last_hidden_state of the image and of a zero image.  `image`:
+        pixel_values [B,3,224,224] (already preprocessed), or anything the pipeline's `feature_extractor` accepts.  The
+        zero-image embedding depends on the weights only: it is computed once per batch size and cached."""
+        if self.image_encoder is None:
+            raise ValueError("encoding the IP-adapter image needs `image_encoder` (instantir_b200.encoders.Dinov2Model)")
+        if output_hidden_states:
+            raise NotImplementedError("the CLIP-vision hidden-state branch (use_clip_encoder) is outside this build's scope")
+        if not torch.is_tensor(image):
+            if self.feature_extractor is None:
+                raise ValueError("non-tensor images need `feature_extractor` (the AutoImageProcessor of dinov2-large)")
+            image = self.feature_extractor(image, return_tensors="pt").pixel_values
+        image_embeds = self.image_encoder(image).last_hidden_state.repeat_interleave(num_images_per_prompt, dim=0)
+        key = tuple(image.shape)
+        if key not in self._zero_image_embeds:
+            self._zero_image_embeds[key] = self.image_encoder(torch.zeros_like(image)).last_hidden_state
+        return image_embeds, self._zero_image_embeds[key].repeat_interleave(num_images_per_prompt, dim=0)
+
+    def prepare_ip_adapter_image_embeds(self, ip_adapter_image, ip_adapter_image_embeds, device=None, num_images_per_prompt=1,
+                                        do_classifier_free_guidance=True):
+        """pipelines/sdxl_instantir.py:672-729 for the single IP-adapter of InstantIR: a list holding one tensor
+        [2, B, S, D] = (zero-image, image) DINOv2 tokens ([1, B, S, D] without CFG)."""
+        if ip_adapter_image_embeds is not None:
+            return ip_adapter_image_embeds if isinstance(ip_adapter_image_embeds, list) else [ip_adapter_image_embeds]
+        if isinstance(ip_adapter_image, list):
+            if len(ip_adapter_image) != 1:
+                raise ValueError(f"`ip_adapter_image` must have same length as the number of IP Adapters. Got {len(ip_adapter_image)} images and 1 IP Adapters.")
+            ip_adapter_image = ip_adapter_image[0]
+        pos, neg = self.encode_image(ip_adapter_image, device, 1)
+        pos, neg = pos.unsqueeze(0), neg.unsqueeze(0)
+        return [torch.cat([neg, pos]) if do_classifier_free_guidance else pos]
 
     def prepare_previewers(self, previewer_lora_path=None, use_lcm=False):
         """Reference: loads previewer_lora_weights.bin into a peft adapter then disables it (:350-397).
@@ -111,7 +210,7 @@ class InstantIRPipeline:
                      negative_pooled_prompt_embeds, ip_adapter_image_embeds, guidance_scale,
                      control_guidance_start, control_guidance_end, previewer_scheduler, preview_start):
         if prompt_embeds is None:
-            raise ValueError("Provide `prompt_embeds` (the CLIP text encoders are outside this build's scope, SURVEY §8 f2).")
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
         if pooled_prompt_embeds is None:
             raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
         if guidance_scale > 1.0 and (negative_prompt_embeds is None or negative_pooled_prompt_embeds is None):
@@ -126,7 +225,8 @@ class InstantIRPipeline:
             raise TypeError("`image` must be a 4-channel latent tensor [B,4,h,w] (pass vae=AutoencoderKL(...) with encoder "
                             "weights to give a 3-channel image instead)")
         if ip_adapter_image_embeds is None:
-            raise ValueError("Provide `ip_adapter_image_embeds` (DINOv2 tokens [2,B,S,D] or a list holding that tensor).")
+            raise ValueError("Provide `ip_adapter_image` / a 3-channel `image` (with image_encoder=Dinov2Model) or `ip_adapter_image_embeds` "
+                             "(DINOv2 tokens [2,B,S,D] or a list holding that tensor).")
         if control_guidance_start >= control_guidance_end:
             raise ValueError(f"control guidance start: {control_guidance_start} cannot be larger or equal to control guidance end: {control_guidance_end}.")
         if control_guidance_start < 0.0:
@@ -149,9 +249,23 @@ class InstantIRPipeline:
                  preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                  controlnet_conditioning_scale=1.0, reference_latents=None, use_cuda_graph=True, cfg_parallel=None,
                  dp_shard=None, record=None, overlap_streams=True, agg_ahead=False, **kwargs):
-        if prompt is not None or negative_prompt is not None or ip_adapter_image is not None:
-            raise NotImplementedError("text / image encoders are outside this build's scope (SURVEY §8 f1-f2): pass "
-                                      "prompt_embeds, pooled_prompt_embeds, ip_adapter_image_embeds and a latent `image`")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please make sure to only forward one of the two.")
+        do_cfg_ = guidance_scale > 1.0
+        if prompt is not None:
+            # 3.1 Encode input prompt (:1327-1346)
+            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
+                prompt, prompt_2, None, num_images_per_prompt, do_cfg_, negative_prompt, negative_prompt_2,
+                negative_prompt_embeds=negative_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
+                clip_skip=kwargs.get("clip_skip"))
+        if ip_adapter_image_embeds is None and (ip_adapter_image is not None or (torch.is_tensor(image) and image.ndim == 4 and image.shape[1] == 3)):
+            # 3.2 Encode ip_adapter_image (:1349-1356); the IP image defaults to the LQ input itself (:1278-1279)
+            src_img = ip_adapter_image
+            if src_img is None:
+                from .encoders import dinov2_preprocess
+
+                src_img = dinov2_preprocess((image.float() + 1.0) / 2.0)
+            ip_adapter_image_embeds = self.prepare_ip_adapter_image_embeds(src_img, None, None, num_images_per_prompt, True)
         if multistep_restore or adastep_restore or denoising_end or reference_latents is not None:
             raise NotImplementedError("multistep_restore / adastep_restore / denoising_end / reference_latents are "
                                       "experimental reference options (SURVEY §8 f4)")

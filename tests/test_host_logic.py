@@ -189,8 +189,14 @@ def test_product_never_imports_oracle_or_reference():
 
 
 def test_pipeline_rejects_out_of_scope_arguments():
+    from types import SimpleNamespace
+
     p = pipeline.InstantIRPipeline.__new__(pipeline.InstantIRPipeline)
-    with pytest.raises(NotImplementedError):
+    p.text_encoder = p.text_encoder_2 = p.tokenizer = p.tokenizer_2 = p.image_encoder = p.feature_extractor = None
+    p.config = SimpleNamespace(force_zeros_for_empty_prompt=True)
+    with pytest.raises(ValueError, match="text_encoder_2"):   # a string prompt needs the encoders + tokenizers
         pipeline.InstantIRPipeline.__call__(p, prompt="a photo")
+    with pytest.raises(ValueError, match="Cannot forward both"):
+        pipeline.InstantIRPipeline.__call__(p, prompt="a photo", prompt_embeds=torch.zeros(1, 77, 8))
     with pytest.raises(NotImplementedError):
         pipeline.InstantIRPipeline.__call__(p, adastep_restore=True)

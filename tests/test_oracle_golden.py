@@ -202,3 +202,33 @@ def test_rescale_noise_cfg_vs_reference_run():
     cfg = g["e_u"] + g["guidance"] * (g["e_c"] - g["e_u"])
     for phi, want in g["out"].items():
         assert torch.equal(opipe.rescale_noise_cfg(cfg, g["e_c"], phi), want), phi
+
+
+def test_encoders_match_transformers_run():
+    """oracle/encoders.py (row f2) vs vectors produced by running the installed `transformers` CLIPTextModel,
+    CLIPTextModelWithProjection and Dinov2Model (tests/golden/make_golden_encoders.py)"""
+    from oracle import encoders as oe
+
+    g = torch.load(os.path.join(G, "encoders.pt"))
+    for name in ("clip_l", "clip_g"):
+        r = g[name]
+        m = oe.CLIPTextModel(**r["cfg"])
+        assert sorted(k for k, _ in m.named_parameters()) == r["names"]
+        seeded_init(m, r["seed"])
+        same_weights(m, r["checksum"])
+        out = m(g["ids"])
+        assert len(out["hidden_states"]) == r["n_hidden"]
+        assert rel(out["hidden_states"][-2], r["penultimate"]) < 2e-6
+        assert rel(out["last_hidden_state"], r["last_hidden_state"]) < 2e-6
+        if name == "clip_l":
+            assert rel(out["pooler_output"], r["pooler_output"]) < 2e-6
+        else:
+            assert rel(out["text_embeds"], r["text_embeds"]) < 2e-6
+    r = g["dinov2"]
+    dm = oe.Dinov2Model(**r["cfg"])
+    assert sorted(k for k, _ in dm.named_parameters()) == r["names"]
+    seeded_init(dm, r["seed"])
+    same_weights(dm, r["checksum"])
+    assert rel(dm(r["x70"]), r["out70"]) < 2e-6
+    assert rel(dm(r["x42"]), r["out42"]) < 2e-6          # interpolated position embeddings, non-square grid
+    assert rel(dm(r["x42"], pos_mode="scale_0.1"), r["out42"]) < 5e-3  # the 4.36.2 variant differs only in the resampling

@@ -269,6 +269,11 @@ int iir_cfg_ddpm_step(const void* eps_uncond, const void* eps_cond, int eps_dtyp
  * with torch.std (unbiased) over each sample of n_per elements; eps fp32 [n_samples, n_per].                      */
 int iir_cfg_rescale(const float* eps_uncond, const float* eps_cond, float* out, int64_t n_samples, int64_t n_per,
                     float guidance, float rescale, void* stream);
+/* adastep_restore (pipelines/sdxl_instantir.py:1636-1644, then :1538-1540 of the next step).  Per image b (fp32 [n_img, n_per]):
+ *   preview_factor[b] = sum (preview - pred_x0)^2 / sum (preview - previewer_mean)^2;  previewer_mean <- preview;
+ *   cond_scale[r * n_img + b] = clamp(preview_factor[b], 0, next_scale) * next_keep for the n_rep CFG branches of the next step */
+int iir_adastep_update(const float* preview, const float* pred_x0, float* previewer_mean, float* preview_factor,
+                       float* cond_scale, int n_img, int n_rep, int64_t n_per, float next_scale, float next_keep, void* stream);
 /* add_noise (lcm_single_step_scheduler.py:492-513): out = sqrt(abar)*x0 + sqrt(1-abar)*noise */
 int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n, float alpha_prod_t,
                   void* stream);

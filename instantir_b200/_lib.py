@@ -30,7 +30,7 @@ SYMBOLS = [
     "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add", "iir_scale",
     "iir_timestep_embedding", "iir_linear_small", "iir_embed_tokens", "iir_patchify", "iir_vit_assemble",
-    "iir_step_prologue", "iir_lcm_step", "iir_cfg_ddpm_step", "iir_cfg_rescale", "iir_add_noise", "iir_gaussian_sample",
+    "iir_step_prologue", "iir_adastep_update", "iir_lcm_step", "iir_cfg_ddpm_step", "iir_cfg_rescale", "iir_add_noise", "iir_gaussian_sample",
 ]
 
 
@@ -117,6 +117,7 @@ def _declare(lib):
     lib.iir_embed_tokens.argtypes = [vp, i, i, vp, i, vp, i, vp, vp]
     lib.iir_patchify.argtypes = [vp, i, i, i, i, i, vp, i, i, vp]
     lib.iir_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    lib.iir_adastep_update.argtypes = [vp, vp, vp, vp, vp, i, i, i64, f, f, vp]
     lib.iir_cfg_rescale.argtypes = [vp, vp, vp, i64, i64, f, f, vp]
     lib.iir_gaussian_sample.argtypes = [vp, vp, vp, i64, i64, f, vp]
     lib.iir_lcm_step.argtypes = [vp, i, vp, vp, i64, f, f, f, vp]

@@ -131,6 +131,44 @@ step_prologue_kernel(const float* __restrict__ latents, long long n4, int n_rep,
   }
 }
 
+// adastep_restore (pipelines/sdxl_instantir.py:1636-1644 and :1538-1540 of the NEXT step), one CTA per image:
+//   pred_x0_l2 = sum (preview - pred_x0)^2, previewer_l2 = sum (preview - previewer_mean)^2 (fp32 tensors, fp64 sums),
+//   preview_factor = pred_x0_l2 / previewer_l2, previewer_mean <- preview,
+//   cond_scale[r * n_img + b] = clamp(preview_factor, 0, next_scale) * next_keep for every CFG branch r of the next step.
+__global__ void __launch_bounds__(1024)
+adastep_kernel(const float* __restrict__ preview, const float* __restrict__ pred_x0, float* __restrict__ previewer_mean,
+               float* __restrict__ preview_factor, float* __restrict__ cond_scale, int n_img, int n_rep, long long n_per,
+               float next_scale, float next_keep) {
+  __shared__ double red[2][32];
+  const int b = blockIdx.x;
+  const float* pv = preview + b * n_per;
+  const float* x0 = pred_x0 + b * n_per;
+  float* pm = previewer_mean + b * n_per;
+  double s0 = 0.0, s1 = 0.0;
+  for (long long i = threadIdx.x; i < n_per; i += 1024) {
+    const float p = pv[i], d0 = p - x0[i], d1 = p - pm[i];
+    s0 += static_cast<double>(d0) * d0;
+    s1 += static_cast<double>(d1) * d1;
+    pm[i] = p;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+  }
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; }  // fixed order
+    const float f = static_cast<float>(t0) / static_cast<float>(t1);
+    preview_factor[b] = f;
+    const float cs = fminf(fmaxf(f, 0.0f), next_scale) * next_keep;
+    for (int r = 0; r < n_rep; ++r) cond_scale[r * n_img + b] = cs;
+  }
+}
+
 int grid_for4(long long n4) {
   long long b = (n4 + 255) / 256;
   long long cap = 8LL * sm_count();
@@ -186,6 +224,18 @@ extern "C" int iir_step_prologue(const float* latents, int64_t n, int n_rep, flo
                                                           n_cond);
   count_launch();
   return check_launch("iir_step_prologue");
+}
+
+extern "C" int iir_adastep_update(const float* preview, const float* pred_x0, float* previewer_mean, float* preview_factor,
+                                  float* cond_scale, int n_img, int n_rep, int64_t n_per, float next_scale, float next_keep,
+                                  void* stream) {
+  IIR_REQUIRE(preview && pred_x0 && previewer_mean && preview_factor && cond_scale && n_img > 0 && n_rep >= 1 && n_per > 0,
+              "iir_adastep_update: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adastep_kernel<<<static_cast<unsigned>(n_img), 1024, 0, st>>>(preview, pred_x0, previewer_mean, preview_factor, cond_scale, n_img,
+                                                                 n_rep, static_cast<long long>(n_per), next_scale, next_keep);
+  count_launch();
+  return check_launch("iir_adastep_update");
 }
 
 extern "C" int iir_add_noise(const float* x0, const float* noise, float* out, int64_t n,

@@ -443,6 +443,17 @@ def vit_assemble(patches, cls, pos, out, *, n_img: int, P: int):
     return out
 
 
+def adastep_update(preview, pred_x0, previewer_mean, preview_factor, cond_scale, *, n_rep: int, next_scale: float, next_keep: float):
+    """adastep_restore bookkeeping of one step (see iir_adastep_update); every tensor fp32, updated in place"""
+    lib = _L()
+    for t, n in ((preview, "preview"), (pred_x0, "pred_x0"), (previewer_mean, "previewer_mean"), (preview_factor, "preview_factor"),
+                 (cond_scale, "cond_scale")):
+        _f32c(t, n)
+    B = pred_x0.shape[0]
+    _lib.check(lib.iir_adastep_update(_p(preview), _p(pred_x0), _p(previewer_mean), _p(preview_factor), _p(cond_scale), B, n_rep,
+                                      pred_x0[0].numel(), float(next_scale), float(next_keep), _stream()), "iir_adastep_update", lib)
+
+
 def timestep_embedding(t, dim: int, out):
     lib = _L(out)
     _f32c(t, "t")

@@ -266,9 +266,12 @@ class InstantIRPipeline:
 
                 src_img = dinov2_preprocess((image.float() + 1.0) / 2.0)
             ip_adapter_image_embeds = self.prepare_ip_adapter_image_embeds(src_img, None, None, num_images_per_prompt, True)
-        if multistep_restore or adastep_restore or denoising_end or reference_latents is not None:
-            raise NotImplementedError("multistep_restore / adastep_restore / denoising_end / reference_latents are "
-                                      "experimental reference options (SURVEY §8 f4)")
+        if multistep_restore or denoising_end or reference_latents is not None:
+            raise NotImplementedError("multistep_restore (calls scheduler.step with kwargs stock DDPM does not have: not runnable in the "
+                                      "reference as shipped, SURVEY App. E) / denoising_end / reference_latents are not built (SURVEY §8 f4)")
+        if adastep_restore and (cfg_parallel is not None or agg_ahead):
+            raise NotImplementedError("adastep_restore with cfg_parallel / agg_ahead: the adaptive factor lives on the cond rank and "
+                                      "makes the Aggregator's schedule data dependent")
         if output_type != "latent":
             if self.vae is None:
                 raise ValueError("output_type != 'latent' needs a VAE: InstantIRPipeline(unet, aggregator, scheduler, vae=AutoencoderKL(...))")
@@ -366,6 +369,8 @@ class InstantIRPipeline:
             S.t_dev = torch.empty(1, **f32)
             S.cond_scale = torch.empty(nb, **f32)
             S.preview_latent = torch.empty(nb, 4, h, w, **f32)
+            S.previewer_mean = torch.zeros(B, 4, h, w, **f32)  # adastep_restore state (:1488-1492)
+            S.preview_factor = torch.ones(B, **f32)
             S.st = SimpleNamespace(down=None, mid=None)
             self._graphs = {key: S}  # one shape at a time: drop graphs of other shapes
             prompt_all, image_all = S.prompt_all, S.image_all
@@ -485,7 +490,11 @@ class InstantIRPipeline:
         g_preview, g_agg_prev, g_agg_lq, g_unet_res, g_unet_plain = S.g_preview, S.g_agg_prev, S.g_agg_lq, S.g_unet_res, S.g_unet_plain
         g_step = S.g_step if overlap_streams else None
         unet.refresh_context(S.prompt_all, S.added, None)
-        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts, ahead=None)
+        if adastep_restore:
+            S.previewer_mean.zero_()
+            S.preview_factor.fill_(1.0)
+            S.cond_scale.fill_(min(1.0, float(scales[0])) * keep[0])
+        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts, ahead=None, last_previewed=False)
         ahead_ok = g_step is not None and agg_ahead
 
         def lq_step(j):
@@ -497,8 +506,16 @@ class InstantIRPipeline:
             t_int = int(ts[i])
             lat = loop.latents
             cs = min(1.0, float(scales[i])) * keep[i]  # preview_factor == 1 without adastep_restore
-            # torch.cat([latents]*2) (:1503; scale_model_input = id), t and cond_scale (:1538-1540) in ONE launch
-            ops.step_prologue(lat, x_in, len(branches), t=float(t_int), t_dev=t_dev, cond_scale=cs, cond_scale_dev=cond_scale)
+            if adastep_restore:
+                # cond_scale = clamp(preview_factor, 0, scale_i) * keep_i per image (:1538-1540) was written on the device by the
+                # previous step's iir_adastep_update; the gate below (:1542) is data dependent, so this option pays the
+                # reference's host sync
+                ops.step_prologue(lat, x_in, len(branches), t=float(t_int), t_dev=t_dev, cond_scale=0.0, cond_scale_dev=None)
+                cs_host = cond_scale.cpu()
+                cs = float(cs_host.max()) if bool((cs_host > 0.1).any()) else min(0.1, float(cs_host.max()))
+            else:
+                # torch.cat([latents]*2) (:1503; scale_model_input = id), t and cond_scale (:1538-1540) in ONE launch
+                ops.step_prologue(lat, x_in, len(branches), t=float(t_int), t_dev=t_dev, cond_scale=cs, cond_scale_dev=cond_scale)
             previewed = False
             noise_pred = None
             if cs > 0.1:  # the `(cond_scale>0.1).sum().item() > 0` gate (:1542), decided on the host
@@ -506,12 +523,14 @@ class InstantIRPipeline:
                     preview_noise = g_preview()
                     previewer_scheduler.step(preview_noise, t_int, x_in, return_dict=False, out=preview_latent)
                     previewed = True
+                    loop.last_previewed = True
                     # the reference keeps the cond chunk (:1564-1567); in a CFG pair only the cond rank holds it
                     if save_preview_row and (cfg_parallel is None or cfg_parallel.branch == 1):
                         loop.preview_row.append(preview_latent[-B:].clone())
                     loop.res_src = "prev"
                 else:
                     loop.res_src = "lq"
+                    loop.last_previewed = False
                 if not previewed and ahead_ok:
                     # Aggregator(t_i) was computed beside the UNet of step i-1 (or is computed now, once per run);
                     # Aggregator(t_{i+1}) runs beside this step's UNet
@@ -540,7 +559,7 @@ class InstantIRPipeline:
                 if cs > 0:
                     raise RuntimeError("control is active but no aggregator features exist")
                 noise_pred = g_unet_plain()  # reference would raise NameError here; UNet-only is the intent
-            elif cs == 0.0:
+            elif cs == 0.0 and not adastep_restore:
                 noise_pred = g_unet_plain()  # stale residuals x 0 (:1602-1603) == no residuals
             else:
                 noise_pred = g_unet_res[loop.res_src]()
@@ -559,7 +578,17 @@ class InstantIRPipeline:
                              guidance=g_step_arg,
                              noise=step_noise[i])
             loop.latents = out.prev_sample
+            if adastep_restore:
+                # :1636-1644 + the next step's clamp (:1538): one launch; `preview` = the cond half of the LAST preview latent
+                # the Aggregator was fed (the LQ latent on non-previewing steps)
+                if loop.res_src is None:
+                    raise RuntimeError("adastep_restore before any controlled step (the reference raises NameError here)")
+                pv = preview_latent[-B:] if loop.last_previewed else S.image_all[-B:]
+                nxt = i + 1 if i + 1 < n else i
+                ops.adastep_update(pv, out.pred_original_sample, S.previewer_mean, S.preview_factor, cond_scale, n_rep=len(branches),
+                                   next_scale=float(scales[nxt]), next_keep=keep[nxt])
             if record is not None:
+                record.setdefault("preview_factor", []).append(S.preview_factor.clone())
                 record.setdefault("latents", []).append(loop.latents.clone())
                 record.setdefault("pred_x0", []).append(out.pred_original_sample.clone())
                 record.setdefault("preview", []).append(preview_latent.clone() if previewed else None)

@@ -37,7 +37,7 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                     preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                     controlnet_conditioning_scale=1.0, generator=None, init_latents_with_lq=True,
                     timesteps=None, record: Optional[dict] = None, guidance_rescale: float = 0.0,
-                    max_steps: Optional[int] = None):
+                    max_steps: Optional[int] = None, adastep_restore: bool = False):
     """Returns the final latents [B,4,h,w]; `record` (if given) collects per-step tensors.
 
     image: LQ latent [B,4,h,w] (the reference accepts 4-channel tensors as latents, :1370-1382).
@@ -66,7 +66,9 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
     else:
         image_embeds = [ip_image_embeds[1].unsqueeze(1)]
     preview_factor = torch.ones((latents.shape[0], 1, 1, 1), dtype=latents.dtype)
+    previewer_mean = torch.zeros_like(latents)  # :1488
     down_res = mid_res = None
+    last_preview = None  # the reference's `preview_latent` is a plain local: it keeps the last gated step's value
     for i, t in enumerate(ts):
         if max_steps is not None and i >= max_steps:  # tests: only the first steps of a long schedule
             break
@@ -89,6 +91,7 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                 unet.disable_adapters()
             else:
                 preview_latent = image
+            last_preview = preview_latent
             down_res, mid_res = aggregator(image, t, encoder_hidden_states=prompt_embeds,
                                            controlnet_cond=preview_latent,
                                            added_cond_kwargs={"text_embeds": add_text_embeds, "time_ids": time_ids},
@@ -105,10 +108,19 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                 noise_pred = rescale_noise_cfg(noise_pred, e_c, guidance_rescale)
         out = scheduler.step(noise_pred, t, latents, generator=generator, return_dict=True)
         latents = out.prev_sample
+        if adastep_restore:  # :1636-1644 (preview_latent is the CFG-concatenated tensor: the cond half is its tail)
+            if last_preview is None:
+                raise RuntimeError("adastep_restore before any controlled step (the reference raises NameError here)")
+            pv = last_preview[latents.shape[0]:] if do_cfg else last_preview
+            pred_x0_l2 = (pv.float() - out.pred_original_sample.float()).pow(2).sum(dim=(1, 2, 3))
+            previewer_l2 = (pv.float() - previewer_mean.float()).pow(2).sum(dim=(1, 2, 3))
+            previewer_mean = pv
+            preview_factor = (pred_x0_l2 / previewer_l2).reshape(-1, 1, 1, 1)
         if record is not None:
             record.setdefault("latents", []).append(latents.clone())
             record.setdefault("pred_x0", []).append(out.pred_original_sample.clone())
             record.setdefault("noise_pred", []).append(noise_pred.clone())
+            record.setdefault("preview_factor", []).append(preview_factor.reshape(-1).clone())
             record.setdefault("preview", []).append(None if preview_latent is None else preview_latent.clone())
     return latents
 

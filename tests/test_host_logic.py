@@ -199,4 +199,4 @@ def test_pipeline_rejects_out_of_scope_arguments():
     with pytest.raises(ValueError, match="Cannot forward both"):
         pipeline.InstantIRPipeline.__call__(p, prompt="a photo", prompt_embeds=torch.zeros(1, 77, 8))
     with pytest.raises(NotImplementedError):
-        pipeline.InstantIRPipeline.__call__(p, adastep_restore=True)
+        pipeline.InstantIRPipeline.__call__(p, multistep_restore=True)

@@ -631,3 +631,21 @@ def test_cfg_rescale_matches_rescale_noise_cfg():
     dims = [1, 2, 3]
     ref = phi * cfg * (c.std(dim=dims, keepdim=True) / cfg.std(dim=dims, keepdim=True)) + (1 - phi) * cfg
     assert rel_l2(out, ref) < 1e-6
+
+
+def test_adastep_update():
+    """iir_adastep_update vs the reference arithmetic (pipelines/sdxl_instantir.py:1636-1644, :1538-1540)"""
+    B, n_rep = 3, 2
+    pv, x0, pm = rnd(B, 4, 16, 24, seed=1), rnd(B, 4, 16, 24, seed=2), rnd(B, 4, 16, 24, seed=3)
+    pm0 = pm.clone()
+    factor = torch.full((B,), float("nan"), device=DEV)
+    cs = torch.full((n_rep * B,), float("nan"), device=DEV)
+    ops.adastep_update(pv, x0, pm, factor, cs, n_rep=n_rep, next_scale=0.8, next_keep=1.0)
+    torch.cuda.synchronize()
+    want = (pv - x0).pow(2).sum((1, 2, 3)) / (pv - pm0).pow(2).sum((1, 2, 3))
+    assert rel_l2(factor, want) < 1e-6
+    assert torch.equal(pm, pv)
+    assert rel_l2(cs, want.clamp(0.0, 0.8).repeat(n_rep)) < 1e-6
+    ops.adastep_update(pv, x0, pm, factor, cs, n_rep=n_rep, next_scale=0.8, next_keep=0.0)   # previewer_mean == preview now: x / 0
+    torch.cuda.synchronize()
+    assert bool(torch.isinf(factor).all()) and float(cs.abs().sum()) == 0.0

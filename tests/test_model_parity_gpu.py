@@ -91,7 +91,7 @@ def test_resampler_vs_reference_vector(precision):
 
 
 def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0, cge=1.0, graph=True, guidance=7.0,
-              timesteps=None, **pipe_kw):
+              timesteps=None, adastep=False, **pipe_kw):
     oc = getattr(ocfg, cfg_name)()
     alpha = 8.0
     ounet, oagg = build_oracle(oc, seed=0, lora_alpha=alpha)
@@ -103,7 +103,8 @@ def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0,
         pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
         ip_image_embeds=inp["ip"], add_time_ids=inp["time_ids"], num_inference_steps=None if timesteps else steps,
         timesteps=timesteps, guidance_scale=guidance,
-        preview_start=preview_start, control_guidance_end=cge, generator=torch.Generator().manual_seed(42), record=rec_o)
+        preview_start=preview_start, control_guidance_end=cge, generator=torch.Generator().manual_seed(42), record=rec_o,
+        adastep_restore=adastep)
     usd, ulora = export_state(ounet)
     asd, _ = export_state(oagg)
     pc = _pcfg_from(oc)
@@ -117,7 +118,7 @@ def _run_pair(precision, cfg_name="tiny", steps=2, B=1, h=32, preview_start=0.0,
                ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=None if timesteps else steps, timesteps=timesteps,
                guidance_scale=guidance,
                previewer_scheduler=LCMSingleStepScheduler(), preview_start=preview_start, control_guidance_end=cge,
-               generator=torch.Generator().manual_seed(42), use_cuda_graph=graph, record=rec_p, **pipe_kw)
+               generator=torch.Generator().manual_seed(42), use_cuda_graph=graph, record=rec_p, adastep_restore=adastep, **pipe_kw)
     torch.cuda.synchronize()
     return ref, rec_o, out.images, rec_p
 
@@ -306,6 +307,25 @@ def test_guidance_rescale_fp32():
         generator=torch.Generator().manual_seed(42), guidance_rescale=0.7, **kw).images
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol,preview_start", [("fp32", 1e-4, 0.0), ("fp32", 1e-4, 0.5), ("fp16", 1e-2, 0.0)])
+def test_adastep_restore(precision, tol, preview_start):
+    """adastep_restore (pipelines/sdxl_instantir.py:1636-1644): the per-image preview_factor
+    = |preview - pred_x0|^2 / |preview - previous preview|^2 scales (clamped) the next step's residuals; B = 2 so the two
+    images get different factors.  preview_start = 0.5: the first two steps feed the Aggregator the LQ latent."""
+    ref, rec_o, out, rec_p = _run_pair(precision, steps=4, B=2, preview_start=preview_start, adastep=True, graph=True)
+    for i, (a, b) in enumerate(zip(rec_p["preview_factor"], rec_o["preview_factor"])):
+        a = a.cpu()
+        # a step whose cond_scale fell below the 0.1 gate re-uses the previous preview: |preview - previous preview|^2 = 0 and
+        # the factor is +inf in the reference too (then clamped to the step's scale)
+        assert torch.equal(torch.isinf(a), torch.isinf(b)), f"preview_factor, step {i}: {a.tolist()} vs {b.tolist()}"
+        fin = torch.isfinite(b)
+        if bool(fin.any()):
+            assert rel_l2(a[fin], b[fin]) < 10 * tol, f"preview_factor, step {i}: {a.tolist()} vs {b.tolist()}"
+    assert float((rec_o["preview_factor"][1] - 1.0).abs().min()) > 1e-3  # the factor really moves: the check is not vacuous
+    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+        assert rel_l2(a, b) < tol, f"step {i}"
 
 
 def test_guidance_scale_le_1_disables_cfg_fp32():

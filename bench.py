@@ -403,11 +403,61 @@ def run_ours(args):
         del vae, img, himg
         torch.cuda.empty_cache()
 
+    step_flops = FLOPS_STEP.get(wl)
+    partitions = None
+
+    def base_line():
+        """the JSON line as far as the main measurement determines it (the roofline leg, the alternate-precision leg and
+        the CPU baseline are added by rank 0 afterwards)"""
+        return {
+            "metric": {"config1": "256x256 restored images per second (30-step schedule, CFG 7)",
+                       "config5": "2048x2048 restored images per second (30 steps, CFG 7)"}.get(wl, METRIC_TEXT),
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[wl],
+                       "images_per_rank": B, "parallelism": ("cfg-parallel pairs x dp" if cfgp else f"dp{world}"),
+                       "step": STEP_TEXT + (" + previewer UNet fwd + LCM" if preview else ""),
+                       "l2": "inputs larger than L2: ~8.6 GB of 16-bit weights are streamed every step (L2 = 126 MB)",
+                       "noise": "DDPM variance noise for the image's 30 steps is drawn at call setup (inside e2e; outside the device-timed steps)",
+                       "cuda_graphs": True},
+            "clocks": clocks,
+            "e2e": {"value": n_images / e2e_s, "unit": "img/s", "h2d_bytes_per_step": h2d / STEPS_PER_IMAGE,
+                    "d2h_bytes_per_step": d2h / STEPS_PER_IMAGE, "seconds_per_image_batch": e2e_s,
+                    "note": "copies happen once per image (30 steps); bytes are per denoising step"},
+            "vae_decode": vae_info,
+            "gpu_launches": int(launches),
+            "roofline": None,
+            "step_tflops": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12) if step_flops else None,
+            "step_frac_of_sustained_peak": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12 / world / peak_sus) if step_flops else None,
+            "partitions": partitions,
+            "kernel_breakdown": {},
+            "top_shapes": {},
+        }
+
     # ---- (N >= 2) the partitions that COMMUNICATE (SURVEY §8e, BASELINE configs[2..4]), timed in this same run:
     # every sub-run times one full 30-step image (so the step mix of config 4 is the real one) after 3 warm steps
-    partitions = None
+    guard = None
     if do_partitions:
         partitions = {}
+
+        def _partition_deadline():  # pragma: no cover
+            # Safety net.  A sub-run that fails on ONE rank of a CFG pair leaves its partner inside an all-gather that
+            # never completes (the r02 8-GPU run lost 10 minutes to NCCL's watchdog that way).  The main measurement is
+            # complete at this point, so when the partition phase overruns its deadline rank 0 prints the line with the
+            # sub-records collected so far and every rank leaves; nothing measured is lost and the job ends.
+            if rank == 0:
+                ln = base_line()
+                ln["partitions"] = dict(partitions)
+                ln["partitions_aborted"] = (f"partition phase exceeded its {deadline_s:.0f} s deadline: remaining sub-runs, the "
+                                            "roofline leg and kernel_breakdown were dropped")
+                emit(ln)
+            os._exit(0)
+
+        deadline_s = max(90.0, args.partition_budget + 150.0 - (time.perf_counter() - t_run0))
+        guard = threading.Timer(deadline_s, _partition_deadline)
+        guard.daemon = True
+        guard.start()
         plan = [("config3_cfg_parallel", "config3", 1, True), ("config3_data_parallel", "config3", 1, False)]
         if world >= 8:
             # config 4 = 64 images: timed as ONE pass of 4 images per rank (8 per CFG pair), i.e. 32 images in flight — the
@@ -465,6 +515,7 @@ def run_ours(args):
         if "value" in partitions.get("config3_cfg_parallel", {}) and world == 2:
             partitions["config3_cfg_parallel"]["note"] = ("1 image on 2 GPUs (latency partition): compare with config 3 on ONE GPU "
                                                           "(profiles/) for the CFG-parallel efficiency")
+        guard.cancel()
 
     if rank == 0:
         # ---- roofline leg: CUDA events around every launch INSIDE the replayed CUDA graphs (event-record nodes
@@ -524,34 +575,15 @@ def run_ours(args):
             for d in breakdown.values():
                 d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] and d["flops"] else None
                 d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] and d["bytes"] else None
-        step_flops = FLOPS_STEP.get(wl)
-        line = {
-            "metric": {"config1": "256x256 restored images per second (30-step schedule, CFG 7)",
-                       "config5": "2048x2048 restored images per second (30 steps, CFG 7)"}.get(wl, METRIC_TEXT),
-            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[wl],
-                       "images_per_rank": B, "parallelism": ("cfg-parallel pairs x dp" if cfgp else f"dp{world}"),
-                       "step": STEP_TEXT + (" + previewer UNet fwd + LCM" if preview else ""),
-                       "l2": "inputs larger than L2: ~8.6 GB of 16-bit weights are streamed every step (L2 = 126 MB)",
-                       "noise": "DDPM variance noise for the image's 30 steps is drawn at call setup (inside e2e; outside the device-timed steps)",
-                       "cuda_graphs": True},
-            "clocks": clocks,
-            "e2e": {"value": n_images / e2e_s, "unit": "img/s", "h2d_bytes_per_step": h2d / STEPS_PER_IMAGE,
-                    "d2h_bytes_per_step": d2h / STEPS_PER_IMAGE, "seconds_per_image_batch": e2e_s,
-                    "note": "copies happen once per image (30 steps); bytes are per denoising step"},
-            "vae_decode": vae_info,
-            "gpu_launches": int(launches),
+        line = base_line()
+        line.update({
             "roofline": roof,
-            "step_tflops": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12) if step_flops else None,
-            "step_frac_of_sustained_peak": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12 / world / peak_sus) if step_flops else None,
             "partitions": partitions,
             "kernel_breakdown": breakdown,
             # the 16 tensor-core shapes that take the most time in one step (key = kind:M:N:K:paired:epilogue)
             "top_shapes": {k: dict(v, us_per_launch=1e3 * v["ms"] / v["launches"], tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None)
                            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:16]},
-        }
+        })
         alt = "bf16" if args.precision == "fp16" else "fp16"
         if world == 1 and not args.no_alt:
             # the same step on the other 16-bit build: bf16 is faster under the power cap (fewer mantissa bits toggle) but

@@ -24,6 +24,7 @@ What changes versus the reference's loop (same results, fewer launches):
 """
 from __future__ import annotations
 
+import gc
 from types import SimpleNamespace
 from typing import List, Optional
 
@@ -80,8 +81,22 @@ class _Graphed:
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            with torch.cuda.graph(g):
-                self.out = self.fn()
+            # torch.cuda.graph captures in cudaStreamCaptureModeGlobal, and since torch 2.9 it no longer runs the garbage
+            # collector first.  A dead reference cycle that still owns CUDAGraph objects (the step closures of an earlier
+            # shape's graph set) collected DURING this capture would run cudaGraphExecDestroy, which that mode prohibits:
+            # the capture is invalidated ("operation not permitted when stream is capturing (function reset)", seen on one
+            # rank of the 8-GPU run profiles/bench_r02c_n8_with_partitions.json).  So: collect now, and keep the cycle
+            # collector off until the capture has ended.
+            if not torch.cuda.is_current_stream_capturing():
+                gc.collect()
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    self.out = self.fn()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             self.n_launch = _lib.launch_count() - before
             self.graph = g
         self.graph.replay()

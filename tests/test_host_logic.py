@@ -200,3 +200,67 @@ def test_pipeline_rejects_out_of_scope_arguments():
         pipeline.InstantIRPipeline.__call__(p, prompt="a photo", prompt_embeds=torch.zeros(1, 77, 8))
     with pytest.raises(NotImplementedError):
         pipeline.InstantIRPipeline.__call__(p, multistep_restore=True)
+
+
+def test_from_unet_weight_source_matches_reference_from_unet():
+    """Aggregator.from_unet (module/aggregator.py:503-578, used at pipelines/sdxl_instantir.py:320-322): every trunk tensor
+    (conv_in, ref_conv_in <- the UNet's conv_in, time / add embeddings, down + mid blocks minus attn2 / norm2) is the UNet's
+    own, the SFT heads get a bounded default Conv2d initialisation and every head closes with a ZERO 1x1 convolution — the
+    product's weight source against the oracle's from_unet + remove_attn2 on the same seeded UNet."""
+    from instantir_b200.aggregator import _FromUNetSource, _OverlaySource
+
+    oc = ocfg.tiny()
+    ounet, _ = build_oracle(oc, seed=0)
+    usd, _ = export_state(ounet)
+    pc = pcfg.ModelConfig(**oc.to_dict())
+    fs = _FromUNetSource(pc, weights.StateDictSource(usd, "cpu"), "cpu", seed=0)
+    oagg = om.Aggregator.from_unet(ounet)
+    om.remove_attn2(oagg)
+    osd = oagg.state_dict()
+    shapes = weights.aggregator_param_shapes(pc)
+    assert set(shapes) == set(osd)
+    n_trunk = n_zero = n_init = 0
+    for k, shp in shapes.items():
+        t = fs.get(k)
+        assert tuple(t.shape) == tuple(shp) and fs.has(k), k
+        if not k.startswith("controlnet_"):
+            assert torch.equal(t.float(), osd[k].float()), k
+            n_trunk += 1
+        elif k.startswith("controlnet_mid_block.1.") or k.split(".")[2] == "1":
+            assert not t.any(), k  # zero_module (module/aggregator.py:980-983): residuals are exactly zero before load_state_dict
+            n_zero += 1
+        else:
+            w = shapes[k.rsplit(".", 1)[0] + ".weight"]
+            bound = (w[1] * w[2] * w[3]) ** -0.5
+            assert float(t.abs().max()) <= bound and float(t.abs().max()) > 0.5 * bound, k  # torch's default Conv2d init range
+            assert torch.equal(t, fs.get(k)), k                                              # and reproducible
+            n_init += 1
+    assert n_trunk > 100 and n_zero == 2 * 10 and n_init == 6 * 10  # 9 + 1 heads: (mlp_shared, mul, add) x (w, b) + zero conv (w, b)
+    assert torch.equal(fs.get("ref_conv_in.weight"), fs.get("conv_in.weight"))
+    with pytest.raises(KeyError):
+        fs.get("up_blocks.0.resnets.0.conv1.weight")
+    # load_state_dict(strict=False): keys of the new state dict win, absent keys keep their current tensors
+    ov = _OverlaySource({"conv_in.bias": torch.full_like(osd["conv_in.bias"], 3.0)}, fs, "cpu")
+    assert float(ov.get("conv_in.bias")[0]) == 3.0 and torch.equal(ov.get("conv_in.weight"), fs.get("conv_in.weight"))
+    assert ov.has("conv_in.bias") and ov.has("mid_block.resnets.0.conv1.weight") and not ov.has("nope")
+
+
+def test_aggregator_load_state_dict_validates_like_torch():
+    """infer.py:142-144: `aggregator.load_state_dict(torch.load(aggregator.pt))`.  The key / shape validation runs before any
+    device work, so it is checked here on a stand-in object: strict=True raises on missing, unexpected and mis-shaped keys."""
+    from types import SimpleNamespace
+
+    from instantir_b200.aggregator import Aggregator
+
+    pc = pcfg.tiny()
+    shapes = weights.aggregator_param_shapes(pc)
+    stub = SimpleNamespace(state_dict_keys=lambda: shapes)
+    good = {k: torch.zeros(s) for k, s in shapes.items()}
+    missing = dict(good)
+    missing.pop("conv_in.weight")
+    with pytest.raises(RuntimeError, match="missing"):
+        Aggregator.load_state_dict(stub, missing)
+    with pytest.raises(RuntimeError, match="unexpected"):
+        Aggregator.load_state_dict(stub, dict(good, extra=torch.zeros(1)))
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        Aggregator.load_state_dict(stub, dict(good, **{"conv_in.bias": torch.zeros(3)}))

@@ -76,6 +76,44 @@ def test_aggregator_vs_reference_forward_vector(precision):
     assert rel_l2(mid, g["mid"]) < TOL[precision]
 
 
+NOT_YET_RUN_ON_GPU = ("written after the round's GPU budget was spent: the code under test is exercised on the CPU only "
+                      "(tests/test_host_logic.py covers its weight source and validation); non-strict, so an XPASS in the driver's "
+                      "log is the GPU verification")
+
+
+@pytest.mark.xfail(reason=NOT_YET_RUN_ON_GPU, strict=False)
+def test_aggregator_from_unet_then_load_state_dict_fp32():
+    """pipelines/sdxl_instantir.py:320-322 + infer.py:142-144 on the product objects: Aggregator.from_unet(unet) gives
+    exactly-zero residuals (zero 1x1 heads, module/aggregator.py:980-983) and conditioning_scale only scales them;
+    load_state_dict(aggregator.pt keys) then makes it identical to an Aggregator constructed from that state dict."""
+    g = torch.load(os.path.join(G, "aggregator.pt"))
+    oc = ocfg.StepConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["cfg"].items()})
+    ounet = seeded_init(om.load_adapter(om.UNet2DConditionModel(oc)), 11)
+    usd, _ = export_state(ounet)
+    pc = _pcfg_from(oc)
+    unet = UNet2DConditionModel(pc, weights.StateDictSource(usd, DEV), DEV, "fp32")
+    agg = Aggregator.from_unet(unet)
+    i = g["inputs"]
+    kw = dict(controlnet_cond=i["cond"].to(DEV), added_cond_kwargs={"text_embeds": i["pooled"].to(DEV), "time_ids": i["time_ids"].to(DEV)})
+    down, mid = agg(i["sample"].to(DEV), torch.tensor(i["t"]), None, **kw)
+    torch.cuda.synchronize()
+    assert len(down) == 9 and not any(bool(d.any()) for d in down) and not bool(mid.any())
+    oagg = om.Aggregator(oc)
+    om.remove_attn2(oagg)
+    seeded_init(oagg, g["seed"])
+    sd, _ = export_state(oagg)
+    res = agg.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys and agg.weights_version == 1
+    down, mid = agg(i["sample"].to(DEV), torch.tensor(i["t"]), None, **kw)
+    ref = Aggregator(pc, weights.StateDictSource(sd, DEV), DEV, "fp32")
+    rdown, rmid = ref(i["sample"].to(DEV), torch.tensor(i["t"]), None, **kw)
+    half, _ = ref(i["sample"].to(DEV), torch.tensor(i["t"]), None, conditioning_scale=0.5, **kw)
+    torch.cuda.synchronize()
+    for a, b, c, d in zip(down, rdown, g["down"], half):
+        assert torch.equal(a, b) and rel_l2(a, c) < 1e-4 and rel_l2(d, 0.5 * c) < 1e-4
+    assert torch.equal(mid, rmid) and rel_l2(mid, g["mid"]) < 1e-4
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_resampler_vs_reference_vector(precision):
     g = torch.load(os.path.join(G, "resampler.pt"))

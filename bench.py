@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg-parallel]
                     [--workload config1..config5] [--batch B] [--precision fp16|bf16]
-                    [--no-cpu] [--no-alt] [--no-vae] [--no-partitions] [--agg-ahead] [--profiler-range]
+                    [--no-cpu] [--no-alt] [--no-vae] [--no-partitions] [--no-experimental] [--agg-ahead] [--profiler-range]
 
 A "step" is one denoising step of the hot path over one batch of synthetic input:
 Aggregator forward + UNet forward (both CFG branches) + fused CFG/DDPM update (+ previewer UNet
@@ -267,6 +267,43 @@ NCU_TRAFFIC_PER_LAUNCH = 28.4e6
 NCU_TRAFFIC_SOURCE = "profiles/ncu_gemm_tc_full_r01d.txt"
 
 
+def experimental_gn_fuse(args, line):
+    """OPT-IN kernel path, measured in a CHILD process (a fault there cannot touch this run): the same benchmark with
+    IIR_GN_FUSE=1 — GroupNorm statistics accumulated by the producing GEMM / conv epilogue, one-pass GroupNorm (DESIGN.md
+    §3.6; the north star's 'GroupNorm fused into the conv epilogue').  That path was written without GPU access and is off
+    by default; this record is its first measurement: step time, GroupNorm class time, and the latents after one step
+    against this run's default path."""
+    import math
+
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(args.warmup), "--precision",
+           args.precision, "--no-cpu", "--no-alt", "--no-vae", "--no-experimental"]
+    env = dict(os.environ, IIR_GN_FUSE="1")
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+        rows = [ln for ln in r.stdout.strip().split("\n") if ln.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"status": "failed", "returncode": r.returncode, "stderr_tail": r.stderr[-1200:], "seconds": time.perf_counter() - t0}
+        c = json.loads(rows[-1])
+        out = {"status": "ran", "env": "IIR_GN_FUSE=1", "ms_per_step": c["ms_per_step"], "value": c["value"], "unit": c["unit"],
+               "gpu_launches": c["gpu_launches"], "default_path": {"ms_per_step": line["ms_per_step"], "gpu_launches": line["gpu_launches"]},
+               "seconds": time.perf_counter() - t0,
+               "note": "same command in a child process; the default path's numbers are this run's main line"}
+        kb, kb0 = c.get("kernel_breakdown") or {}, line.get("kernel_breakdown") or {}
+        out["norm_kernels_single_stream_ms"] = {"fused": {k: kb[k]["ms"] for k in ("groupnorm", "groupnorm_apply") if k in kb},
+                                                "default": {k: kb0[k]["ms"] for k in ("groupnorm", "groupnorm_apply") if k in kb0}}
+        a, b = c.get("latents_probe_after_step0"), line.get("latents_probe_after_step0")
+        if a and b and len(a["sample"]) == len(b["sample"]):
+            num = math.sqrt(sum((x - y) ** 2 for x, y in zip(a["sample"], b["sample"])))
+            den = math.sqrt(sum(y * y for y in b["sample"])) or 1.0
+            out["latents_after_step0_rel_diff_vs_default"] = num / den
+            out["latents_norm_ratio"] = a["norm"] / b["norm"] if b["norm"] else None
+            out["parity_ok"] = bool(num / den < 5e-3)
+        return out
+    except Exception as e:  # pragma: no cover
+        return {"status": "failed", "error": f"{type(e).__name__}: {str(e)[:400]}", "seconds": time.perf_counter() - t0}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -331,8 +368,14 @@ def run_ours(args):
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     loop = pipe(**devin, generator=gen, prepare_only=True, **call_kw)
     n_sched = loop.n_steps
+    probe = None
     for i in range(args.warmup):
         loop.step(i % n_sched)
+        if i == 0 and rank == 0:
+            # fingerprint of the latents after ONE step from the seeded start (warm-up, untimed): lets a run of an opt-in
+            # kernel path (the experimental_gn_fuse leg below) be compared with this run's default path
+            flat = loop.latents.detach().float().flatten()
+            probe = {"norm": float(flat.norm()), "sample": [float(v) for v in flat[:: max(1, flat.numel() // 64)][:64].cpu()]}
     fence()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -427,6 +470,7 @@ def run_ours(args):
                     "note": "copies happen once per image (30 steps); bytes are per denoising step"},
             "vae_decode": vae_info,
             "gpu_launches": int(launches),
+            "latents_probe_after_step0": probe,
             "roofline": None,
             "step_tflops": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12) if step_flops else None,
             "step_frac_of_sustained_peak": (step_flops * n_images / (ms_per_step * 1e-3) / 1e12 / world / peak_sus) if step_flops else None,
@@ -612,6 +656,8 @@ def run_ours(args):
                 torch.cuda.empty_cache()
             except Exception as e:  # pragma: no cover
                 line[alt] = {"error": str(e)}
+        if world == 1 and wl == "config2" and not args.no_experimental and os.environ.get("IIR_GN_FUSE", "0") != "1":
+            line["experimental_gn_fuse"] = experimental_gn_fuse(args, line)
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -661,6 +707,7 @@ def main():
     ap.add_argument("--partition-budget", type=float, default=240.0, help="seconds of total run time after which no further partition sub-run starts")
     ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode leg (SURVEY §8 f1)")
+    ap.add_argument("--no-experimental", action="store_true", help="N = 1: skip the child-process run of the opt-in fused-GroupNorm path")
     ap.add_argument("--agg-ahead", action="store_true", help="run Aggregator(t_{i+1}) beside the whole UNet(t_i) (previewer-off workloads)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit operand type of the timed run (fp16 = the reference's own and the one that meets the parity bar)")

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IIR_ABI_VERSION 10
+#define IIR_ABI_VERSION 11
 
 typedef enum {
   IIR_OK = 0,
@@ -104,6 +104,16 @@ typedef struct {
   float ln_eps;
   int conv_asym;        /* simt, stride 2 only: pad bottom/right only (diffusers Downsample2D(padding=0) of the VAE
                            encoder: F.pad (0,1,0,1) then a pad-0 stride-2 conv); 0 = symmetric pad 1           */
+  /* ---- GroupNorm statistics from the producing epilogue (tc only, OPT-IN, ABI 11; nn.GroupNorm of ResnetBlock2D /
+   * Transformer2DModel, module/min_sdxl.py:245,250,568,838).  gn_sums [n_samples, gn_groups, 2] int64 fixed-point
+   * accumulators (sum * 2^24, sum of squares * 2^26) that every tile ADDS the partial sums of its final output values into
+   * (integer atomics: order-independent, bit-reproducible); must be ZERO on entry (iir_memset_zero).  The consumer is
+   * iir_groupnorm_apply_sums: the stand-alone statistics pass over the tensor (iir_groupnorm's first kernel) disappears.
+   * Needs pair == NONE, N == gn_groups * gn_cpg with gn_cpg even, the direct-store epilogue (no 16-bit residual), and
+   * rows_per_sample such that the 32 rows of a warp belong to one sample (linear: rows_per_sample % 32 == 0; conv: an
+   * image of >= 32 pixels per tile, i.e. W % 8 == 0 and H >= 4).                                                          */
+  void* gn_sums;
+  int gn_cpg, gn_groups;
 } iir_gemm_args;
 
 /* tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate) */
@@ -165,6 +175,13 @@ int64_t iir_groupnorm_scratch_floats(int n_img, int groups);
 int iir_groupnorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* out,
                   int out_dtype, int n_img, int HW, int C, int groups, float eps, int silu,
                   float* partials, void* stream);
+/* The second half of GroupNorm alone (OPT-IN, ABI 11): normalise + affine [+ SiLU] with (mean, rstd) taken from the
+ * fixed-point sums a producing GEMM / conv accumulated (iir_gemm_args.gn_sums) — one pass over x instead of two.    */
+int iir_groupnorm_apply_sums(const void* x, int x_dtype, const float* gamma, const float* beta, const void* gn_sums,
+                             void* out, int out_dtype, int n_img, int HW, int C, int groups, float eps, int silu,
+                             void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (clears gn_sums arenas inside a captured forward) */
+int iir_memset_zero(void* ptr, int64_t bytes, void* stream);
 /* LayerNorm over the last dim, optional affine (gamma/beta) and optional adaLN modulation
  * out = LN(x) * (1 + mod[b, C:2C]) + mod[b, 0:C]  (module/ip_adapter/attention_processor.py:18-26;
  * module/min_sdxl.py:534-538).                                                              */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstantir_b200.so")            # 16-bit operands: bf16
 LIB_PATH_FP16 = os.path.join(HERE, "libinstantir_b200_fp16.so")  # 16-bit operands: fp16
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 F32, BF16, F16 = 0, 1, 2
 # 16-bit operand type of the default library build: IEEE fp16 is the reference's own inference precision
 # (infer.py:119) and the one that meets the north star's <= 1e-2 per-step latent bar; the bf16
@@ -27,7 +27,7 @@ SYMBOLS = [
     "iir_abi_version", "iir_h16_dtype", "iir_last_error", "iir_launch_count",
     "iir_gemm_tc", "iir_gemm_simt", "iir_conv3x3_direct",
     "iir_attn_workspace_bytes", "iir_attn_tc", "iir_attn_simt",
-    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
+    "iir_groupnorm_scratch_floats", "iir_groupnorm", "iir_groupnorm_apply_sums", "iir_memset_zero", "iir_layernorm", "iir_adaln_batched", "iir_softmax_rows",
     "iir_concat_inject", "iir_upsample2x", "iir_im2col3x3_s2", "iir_cast2d", "iir_silu", "iir_add", "iir_scale",
     "iir_timestep_embedding", "iir_linear_small", "iir_embed_tokens", "iir_patchify", "iir_vit_assemble",
     "iir_step_prologue", "iir_adastep_update", "iir_lcm_step", "iir_cfg_ddpm_step", "iir_cfg_rescale", "iir_add_noise", "iir_gaussian_sample",
@@ -53,6 +53,7 @@ class GemmArgs(C.Structure):
         ("ln_stats_out", C.c_void_p), ("ln_out16", C.c_void_p), ("ld_ln_out16", C.c_int64),
         ("ln_stats_in", C.c_void_p), ("ln_stats_zero", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
         ("conv_asym", C.c_int),
+        ("gn_sums", C.c_void_p), ("gn_cpg", C.c_int), ("gn_groups", C.c_int),
     ]
 
 
@@ -101,6 +102,8 @@ def _declare(lib):
     lib.iir_groupnorm_scratch_floats.argtypes = [i, i]
     lib.iir_groupnorm_scratch_floats.restype = i64
     lib.iir_groupnorm.argtypes = [vp, i, vp, vp, vp, i, i, i, i, i, f, i, vp, vp]
+    lib.iir_groupnorm_apply_sums.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, i, f, i, vp]
+    lib.iir_memset_zero.argtypes = [vp, i64, vp]
     lib.iir_layernorm.argtypes = [vp, i, vp, vp, vp, i64, i, vp, i, i, i, f, vp]
     lib.iir_adaln_batched.argtypes = [vp, i, i, i, vp, i64, f, i, vp]
     lib.iir_softmax_rows.argtypes = [vp, i64, vp, i, i64, i, i, f, vp]

@@ -107,3 +107,10 @@ extern "C" int iir_abi_version(void) { return IIR_ABI_VERSION; }
 extern "C" int iir_h16_dtype(void) { return IIR_H16; }
 extern "C" const char* iir_last_error(void) { return iir::g_err; }
 extern "C" uint64_t iir_launch_count(void) { return iir::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int iir_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  IIR_REQUIRE(ptr && bytes > 0, "iir_memset_zero: bad args");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { iir::set_error("iir_memset_zero: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
+  return IIR_OK;
+}

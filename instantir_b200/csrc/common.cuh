@@ -30,6 +30,13 @@ typedef __nv_bfloat162 h162;
 
 namespace iir {
 
+// GroupNorm statistics accumulated by the producing GEMM / conv epilogue (iir_gemm_args.gn_sums, opt-in): int64 fixed point,
+// sum * 2^24 and sum of squares * 2^26 per (sample, group).  Headroom: |sum| < 2^39 and sum of squares < 2^37 per group
+// (655 360 elements per group at 128² x 40 channels: rms up to ~450); resolution 6e-8 / 1.5e-8 per 32 x 32 partial, i.e.
+// still 0.2 % of a partial whose values are ~1e-4.
+constexpr float GN_S1_SCALE = 16777216.f;  // 2^24
+constexpr float GN_S2_SCALE = 67108864.f;  // 2^26
+
 __host__ __device__ __forceinline__ bool dtype_ok(int d) { return d == IIR_F32 || d == IIR_H16; }
 __device__ __forceinline__ float h16_to_f(h16 v) {
 #if defined(IIR_FP16)

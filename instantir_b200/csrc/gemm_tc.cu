@@ -91,7 +91,24 @@ struct alignas(64) GemmTcParams {
   int wide_out, wide_ln16;  // rows of out / ln_out16 start on 32-byte boundaries: 256-bit stores
   int probe;  // measurement builds only (-DIIR_GEMM_PROBE): 1 = skip the epilogue body, 2 = skip its global stores,
               // 3 = TMEM loads + row-phase math only, 4 = TMEM loads only
+  // GroupNorm statistics of the output accumulated by the epilogue (GNS instantiations only; opt-in)
+  unsigned long long* gn_sums;  // [n_samples][gn_groups][2] int64 fixed point (GN_S1_SCALE / GN_S2_SCALE), zero on entry
+  int gn_cpg, gn_groups;
 };
+
+// One group's partial (sum, sum of squares) of a warp's 32 rows: fixed-order shuffle tree, then two integer atomics by
+// lane 0 (integer adds commute: the totals do not depend on the order in which tiles and warps arrive).
+__device__ __forceinline__ void gn_flush(float s, float q, unsigned long long* acc, int lane) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if (lane == 0) {
+    atomicAdd(acc, static_cast<unsigned long long>(__float2ll_rn(s * GN_S1_SCALE)));
+    atomicAdd(acc + 1, static_cast<unsigned long long>(__float2ll_rn(q * GN_S2_SCALE)));
+  }
+}
 
 struct TileCoord {
   int m0;          // linear: first row
@@ -121,9 +138,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmTcParams& p, int stile
   return c;
 }
 
-template <int PAIR, int CL, bool MMA2, int EW>
+template <int PAIR, int CL, bool MMA2, int EW, bool GNS = false>
 __global__ void __launch_bounds__(gemm_threads(EW), EW == 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+  static_assert(!GNS || (PAIR == 0 && EW == 8), "GroupNorm statistics: plain epilogue, 8 epilogue warps");
   static_assert(!MMA2 || CL == 2, "cta_group::2 needs a 2-CTA cluster");
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
   constexpr int TMEM_COLS = EW == 4 ? 256 : 512;
@@ -553,6 +571,31 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
             if (p.ln_out16) st16(reinterpret_cast<h16*>(p.ln_out16) + m_own * p.ld_ln16 + on, p.wide_ln16);
           }
+          if constexpr (GNS) {
+            // GroupNorm partial sums of this warp's 32 rows x (up to) 32 final output values each.  The host guarantees
+            // that the 32 rows belong to ONE sample; rows outside the matrix contribute zeros.  Group boundaries fall on
+            // even columns (gn_cpg is even, chunks start on multiples of 32), so the branch below is warp-uniform.
+            const int glim = min(ncols - cc, n_out_total - on);  // valid columns of this chunk
+            const int smp = __reduce_max_sync(0xffffffffu, valid ? sample : 0);
+            unsigned long long* gacc = p.gn_sums + static_cast<long long>(smp) * p.gn_groups * 2;
+            int g = on / p.gn_cpg;
+            int next = (g + 1) * p.gn_cpg - on;  // first column (relative to `on`) of the next group
+            float gs = 0.f, gq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              if (j == next && j < glim) {  // a group ends in front of column j and valid columns follow
+                gn_flush(gs, gq, gacc + 2 * g, lane);
+                gs = gq = 0.f;
+                ++g;
+                next += p.gn_cpg;
+              }
+              if (valid && j < glim) {
+                gs += v[j] + v[j + 1];
+                gq = fmaf(v[j], v[j], fmaf(v[j + 1], v[j + 1], gq));
+              }
+            }
+            if (glim > 0) gn_flush(gs, gq, gacc + 2 * g, lane);
+          }
           if (EARLY_LD && kc + 1 < nchunks_w) issue_ld(kc + 1);
           if (pre) {
             __syncwarp();  // every lane has read its row of the slot before the next prefetch overwrites it
@@ -817,6 +860,21 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     IIR_REQUIRE(!a->ln_stats_zero, "iir_gemm_tc: ln_stats_zero needs ln_stats_in");
   }
 
+  if (a->gn_sums) {
+    // GroupNorm statistics from this launch's epilogue (opt-in): see iir_gemm_args.gn_sums
+    IIR_REQUIRE(a->pair == IIR_PAIR_NONE && !a->ln_stats_out && p.direct,
+                "iir_gemm_tc: gn_sums needs a plain epilogue on the direct-store path (no pair, no LayerNorm producer, no 16-bit residual)");
+    IIR_REQUIRE(a->gn_cpg >= 2 && a->gn_cpg % 2 == 0 && a->gn_groups > 0 && a->gn_groups * a->gn_cpg == a->N,
+                "iir_gemm_tc: gn_sums needs N == gn_groups * gn_cpg with an even gn_cpg (N=%d groups=%d cpg=%d)", a->N, a->gn_groups, a->gn_cpg);
+    IIR_REQUIRE((reinterpret_cast<uintptr_t>(a->gn_sums) & 7) == 0, "iir_gemm_tc: gn_sums must be 8-byte aligned");
+    IIR_REQUIRE(cl == 1 || mma2, "iir_gemm_tc: gn_sums is built for single CTAs and cta_group::2 pairs only");
+    // the 32 rows of an epilogue warp must belong to one sample
+    if (a->conv) IIR_REQUIRE(p.Wt * p.Ht >= 32, "iir_gemm_tc: gn_sums needs >= 32 pixels of one image per tile (H=%d W=%d)", a->H, a->W);
+    else IIR_REQUIRE(p.rows_per_sample % 32 == 0, "iir_gemm_tc: gn_sums needs rows_per_sample %% 32 == 0 (got %d)", p.rows_per_sample);
+    p.gn_sums = reinterpret_cast<unsigned long long*>(a->gn_sums);
+    p.gn_cpg = a->gn_cpg; p.gn_groups = a->gn_groups;
+  }
+
   const int stage_bytes = A_STAGE_BYTES + (mma2 ? a->bn / 2 : a->bn) * BK * 2;
   // half-SM variant: only for launches that are a single wave of CTAs anyway (one accumulator buffer: no epilogue /
   // main-loop overlap between tiles of a CTA) and whose pipeline still gets >= 3 stages in 113 KB
@@ -826,7 +884,7 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
     half_env = e ? atoi(e) : 0;
   }
   int ew = 8;
-  if (half_env == 1 && p.tiles_m_cl * p.tiles_n * cl <= sm_count() &&
+  if (half_env == 1 && !a->gn_sums && p.tiles_m_cl * p.tiles_n * cl <= sm_count() &&
       (smem_budget(4) - 1024 - 256 - VEC_BYTES - 4 * EPI_STAGE_BYTES) / stage_bytes >= 3)
     ew = 4;
   const int CH_STRIDE = 32 * (ew / 4), SMEM_BUDGET = smem_budget(ew), EW = ew;
@@ -876,10 +934,20 @@ extern "C" int iir_gemm_tc(const iir_gemm_args* a, void* stream) {
   else if (cl == 4) { LAUNCH2(PAIRV, 4, false) }     \
   else if (cl == 2) { LAUNCH2(PAIRV, 2, false) }     \
   else { LAUNCH2(PAIRV, 1, false) }
-  if (a->pair == IIR_PAIR_NONE) { LAUNCH(0) }
+#define LAUNCH_GNS(CLV, M2)                                                                                       \
+  e = cudaFuncSetAttribute(gemm_tc_kernel<0, CLV, M2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           (int)smem);                                                                            \
+  if (e == cudaSuccess)                                                                                           \
+    e = launch_cluster_pdl(gemm_tc_kernel<0, CLV, M2, 8, true>, dim3(grid), dim3(gemm_threads(8)), smem, st, CLV, p);
+  if (a->gn_sums) {
+    if (mma2) { LAUNCH_GNS(2, true) }
+    else { LAUNCH_GNS(1, false) }
+  }
+  else if (a->pair == IIR_PAIR_NONE) { LAUNCH(0) }
   else if (a->pair == IIR_PAIR_GEGLU) { LAUNCH(1) }
   else if (a->pair == IIR_PAIR_SFT) { LAUNCH(2) }
   else { set_error("iir_gemm_tc: bad pair=%d", a->pair); return IIR_ERR_INVALID; }
+#undef LAUNCH_GNS
 #undef LAUNCH
 #undef LAUNCH2
 #undef LAUNCH3

@@ -168,27 +168,13 @@ gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partials, float* __
 }
 
 // ---- stage 2: normalise, affine, optional SiLU ---------------------------------------------
+// the row loop shared by gn_apply_kernel and gn_apply_sums_kernel: per-channel (scale, shift) are in shared memory
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const float* __restrict__ stats,
-                TO* __restrict__ out, int HW, int C, int groups, int silu, int rows_per_block, int TX, int TY) {
+__device__ __forceinline__ void gn_apply_rows(const TI* __restrict__ x, TO* __restrict__ out, const float* s_scale,
+                                              const float* s_shift, int HW, int C, int silu, int rows_per_block, int TX,
+                                              int TY) {
   constexpr int N = V16<TI>::N;
-  extern __shared__ float sm[];  // [C] scale, [C] shift
-  pdl_trigger();
-  pdl_wait();
-  float* s_scale = sm;
-  float* s_shift = sm + C;
   const int img = blockIdx.y;
-  const int cpg = C / groups;
-  const float* s_stats = stats + static_cast<long long>(img) * groups * 2;  // (mean, rstd) pairs
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = s_stats[2 * g + 1] * (gamma ? gamma[c] : 1.0f);
-    s_scale[c] = sc;
-    s_shift[c] = (beta ? beta[c] : 0.0f) - s_stats[2 * g] * sc;
-  }
-  __syncthreads();
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int cv = ty < TY ? C / N : 0;
   const int r0 = blockIdx.x * rows_per_block;
@@ -234,6 +220,58 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
       stv<N>(optr, a);
     }
   }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ stats,
+                TO* __restrict__ out, int HW, int C, int groups, int silu, int rows_per_block, int TX, int TY) {
+  extern __shared__ float sm[];  // [C] scale, [C] shift
+  pdl_trigger();
+  pdl_wait();
+  float* s_scale = sm;
+  float* s_shift = sm + C;
+  const int img = blockIdx.y;
+  const int cpg = C / groups;
+  const float* s_stats = stats + static_cast<long long>(img) * groups * 2;  // (mean, rstd) pairs
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_stats[2 * g + 1] * (gamma ? gamma[c] : 1.0f);
+    s_scale[c] = sc;
+    s_shift[c] = (beta ? beta[c] : 0.0f) - s_stats[2 * g] * sc;
+  }
+  __syncthreads();
+  gn_apply_rows<TI, TO>(x, out, s_scale, s_shift, HW, C, silu, rows_per_block, TX, TY);
+}
+
+// The same pass with (mean, rstd) derived in the prologue from the fixed-point (sum, sum of squares) a producing GEMM / conv
+// epilogue accumulated per (sample, group) (iir_gemm_args.gn_sums): the statistics pass over x disappears.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_sums_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const long long* __restrict__ sums, TO* __restrict__ out, int HW, int C, int groups, double inv_count,
+                     float eps, int silu, int rows_per_block, int TX, int TY) {
+  extern __shared__ float sm[];  // [C] scale, [C] shift
+  pdl_trigger();
+  pdl_wait();
+  float* s_scale = sm;
+  float* s_shift = sm + C;
+  const int img = blockIdx.y;
+  const int cpg = C / groups;
+  const long long* s_sums = sums + static_cast<long long>(img) * groups * 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = static_cast<double>(__ldcg(s_sums + 2 * g)) * (1.0 / GN_S1_SCALE) * inv_count;
+    double var = static_cast<double>(__ldcg(s_sums + 2 * g + 1)) * (1.0 / GN_S2_SCALE) * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = rstd * (gamma ? gamma[c] : 1.0f);
+    s_scale[c] = sc;
+    s_shift[c] = (beta ? beta[c] : 0.0f) - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+  gn_apply_rows<TI, TO>(x, out, s_scale, s_shift, HW, C, silu, rows_per_block, TX, TY);
 }
 
 // ---- LayerNorm: one warp per row, row cached in registers ----------------------------------
@@ -492,6 +530,46 @@ extern "C" int iir_groupnorm(const void* x, int x_dtype, const float* gamma, con
   if (e != cudaSuccess) { set_error("iir_groupnorm: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
   count_launch();
   return check_launch("iir_groupnorm(apply)");
+}
+
+extern "C" int iir_groupnorm_apply_sums(const void* x, int x_dtype, const float* gamma, const float* beta, const void* gn_sums,
+                                        void* out, int out_dtype, int n_img, int HW, int C, int groups, float eps, int silu,
+                                        void* stream) {
+  IIR_REQUIRE(x && out && gn_sums, "iir_groupnorm_apply_sums: null pointer");
+  IIR_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype), "iir_groupnorm_apply_sums: unsupported dtype for this library build");
+  IIR_REQUIRE(n_img > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64 && C % groups == 0 && C % 4 == 0,
+              "iir_groupnorm_apply_sums: bad shape n=%d HW=%d C=%d G=%d", n_img, HW, C, groups);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int vecn = x_dtype == IIR_F32 ? 4 : 8;
+  IIR_REQUIRE(C % vecn == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(gn_sums) & 7) == 0,
+              "iir_groupnorm_apply_sums: C=%d must be a multiple of %d, x/out 16-byte and gn_sums 8-byte aligned", C, vecn);
+  IIR_REQUIRE(2 * (size_t)C * sizeof(float) <= 48 * 1024, "iir_groupnorm_apply_sums: C=%d too large", C);
+  // the thread layout of iir_groupnorm's second kernel
+  const int cv = C / vecn;
+  const int passes = (cv + GN_THREADS - 1) / GN_THREADS;
+  const int TX = (cv + passes - 1) / passes;
+  const int TY = GN_THREADS / TX < 1 ? 1 : GN_THREADS / TX;
+  const int threads = (TX * TY + 31) / 32 * 32;
+  int blocks = (6 * sm_count() + n_img - 1) / n_img;
+  int rpb = (HW + blocks - 1) / blocks;
+  if (rpb < 8 * TY) rpb = 8 * TY;
+  if (rpb > HW) rpb = HW;
+  dim3 g2((HW + rpb - 1) / rpb, n_img);
+  const double inv_count = 1.0 / (static_cast<double>(HW) * (C / groups));
+  cudaError_t e;
+#define GO(TI, TO)                                                                                                    \
+  e = launch_pdl(gn_apply_sums_kernel<TI, TO>, g2, dim3(threads), 2 * (size_t)C * sizeof(float), st,                  \
+                 reinterpret_cast<const TI*>(x), gamma, beta, reinterpret_cast<const long long*>(gn_sums),             \
+                 reinterpret_cast<TO*>(out), HW, C, groups, inv_count, eps, silu, rpb, TX, TY)
+  if (x_dtype == IIR_F32 && out_dtype == IIR_F32) GO(float, float);
+  else if (x_dtype == IIR_F32 && out_dtype == IIR_H16) GO(float, bf16);
+  else if (x_dtype == IIR_H16 && out_dtype == IIR_F32) GO(bf16, float);
+  else GO(bf16, bf16);
+#undef GO
+  if (e != cudaSuccess) { set_error("iir_groupnorm_apply_sums: %s", cudaGetErrorString(e)); return IIR_ERR_CUDA; }
+  count_launch();
+  return check_launch("iir_groupnorm_apply_sums");
 }
 
 extern "C" int iir_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta,

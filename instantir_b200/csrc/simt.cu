@@ -476,6 +476,7 @@ extern "C" int iir_gemm_simt(const iir_gemm_args* a, void* stream) {
   IIR_REQUIRE(dtype_ok(a->a_dtype) && dtype_ok(a->w_dtype) && dtype_ok(a->out_dtype) && (!a->residual || dtype_ok(a->res_dtype)) && (!a->aux || dtype_ok(a->aux_dtype)), "iir_gemm_simt: unsupported dtype for this library build (fp32 or %s only)", IIR_H16 == IIR_F16 ? "fp16" : "bf16");
   IIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "iir_gemm_simt: empty problem");
   IIR_REQUIRE(!a->ln_stats_out && !a->ln_out16 && !a->ln_stats_in, "iir_gemm_simt: folded LayerNorm is a tcgen05-path feature (the check mode runs iir_layernorm)");
+  IIR_REQUIRE(!a->gn_sums, "iir_gemm_simt: gn_sums is a tcgen05-path feature (the check mode runs iir_groupnorm)");
   IIR_REQUIRE(a->pair == IIR_PAIR_NONE || (a->bn > 0 && a->bn % 2 == 0 && a->N % a->bn == 0),
               "iir_gemm_simt: paired epilogue needs N%%bn==0");
   GemmSimtParams p;

@@ -10,6 +10,7 @@ star's check mode (everything fp32, SIMT kernels).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -35,12 +36,37 @@ class Runtime:
         self.lora_enabled = False
         self.temb_bank = SmallLinearBank(self)    # resnet time_emb_proj (input: silu(emb))
         self.adaln_bank = SmallLinearBank(self)   # adaLN linears of the IP-adapter processors (input: silu(temb))
+        # OPT-IN (IIR_GN_FUSE=1, tcgen05 path only): GroupNorm statistics are accumulated by the epilogue of
+        # the GEMM / conv that PRODUCES the tensor, so GroupNorm is one pass (iir_groupnorm_apply_sums) instead of two.
+        # Not yet verified on a GPU: off by default.
+        self.gn_fuse = self.tc and os.environ.get("IIR_GN_FUSE", "0") == "1"
+        self._gn_arena, self._gn_used = None, 0
+
+    GN_ARENA_WORDS = 1 << 16  # int64 words: 67 GroupNorm sites x (CFG batch x 32 groups x 2) fits 8 images per forward
 
     def new_forward(self):
         """start of a model forward: per-forward caches are dropped"""
         self._silu_cache = None
         self.temb_bank.reset()
         self.adaln_bank.reset()
+        if self.gn_fuse:
+            if self._gn_arena is None:
+                self._gn_arena = torch.zeros(self.GN_ARENA_WORDS, device=self.device, dtype=torch.int64)
+            # every accumulator of the forward is cleared by ONE memset node at its start
+            ops.memset_zero(self._gn_arena)
+            self._gn_used = 0
+
+    def gn_site(self, n_img: int, groups: int):
+        """a zeroed [n_img, groups, 2] int64 accumulator for one GroupNorm input of this forward (None when the arena is
+        exhausted: the caller falls back to the two-kernel GroupNorm)"""
+        if not self.gn_fuse or self._gn_arena is None:
+            return None
+        n = n_img * groups * 2
+        if self._gn_used + n > self._gn_arena.numel():
+            return None
+        t = self._gn_arena[self._gn_used:self._gn_used + n].view(n_img, groups, 2)
+        self._gn_used += n
+        return t
 
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.device, dtype=dtype or self.act_dtype)
@@ -58,6 +84,7 @@ class FMap:
     H: int
     W: int
     C: int
+    gn: Optional[torch.Tensor] = None  # GroupNorm (sum, sum of squares) accumulated by the kernel that produced `t` (opt-in)
 
     @property
     def M(self):
@@ -168,7 +195,8 @@ class Linear:
         self.folded = fold is not None
         self.N, self.K = self.w.base.shape
 
-    def __call__(self, a, M, out=None, out_dtype=None, residual=None, act=ops.ACT_NONE, ln_out=None):
+    def __call__(self, a, M, out=None, out_dtype=None, residual=None, act=ops.ACT_NONE, ln_out=None, gn=None,
+                 rows_per_sample=0):
         rt = self.rt
         if out is None:
             out = torch.empty(M, self.N, device=rt.device, dtype=out_dtype or rt.act_dtype)
@@ -179,7 +207,7 @@ class Linear:
                      tc=True, ln_in=(a, self.w.colsum.get(), a.eps))
         else:
             ops.gemm(a, self.w.get(), out, M=M, N=self.N, K=self.K, bias=self.b, residual=residual, act=act, tc=rt.tc,
-                     ln_out=ln_out)
+                     ln_out=ln_out, gn=gn, rows_per_sample=rows_per_sample)
         return out
 
 
@@ -279,7 +307,10 @@ class Conv3x3:
         self.Cout = self.w.base.shape[0]
         self.Cin = self.w.base.shape[1] // 9
 
-    def __call__(self, x: FMap, out_dtype=None, rowvec=None, residual=None, act=ops.ACT_NONE, up2=False) -> FMap:
+    def __call__(self, x: FMap, out_dtype=None, rowvec=None, residual=None, act=ops.ACT_NONE, up2=False,
+                 gn_groups: int = 0) -> FMap:
+        """gn_groups > 0 (opt-in path): the epilogue also accumulates the GroupNorm statistics of the output, returned as
+        FMap.gn, when the launch qualifies (stride 1, tcgen05 path)"""
         rt = self.rt
         H, W = (2 * x.H, 2 * x.W) if up2 else (x.H, x.W)
         Ho, Wo = (H - 1) // self.stride + 1, (W - 1) // self.stride + 1
@@ -302,13 +333,24 @@ class Conv3x3:
             if self.stride == 2:
                 cols = rt.empty(M, 9 * self.Cin)
                 ops.im2col3x3_s2(src.t, cols, n_img=x.n, H=H, W=W, C=self.Cin, asym=self.asym)
-                ops.gemm(cols, self.w.get(), out, tc=True, **kw)
+                gn = None
+                if gn_groups and rt.gn_fuse and act == ops.ACT_NONE and ops.gn_eligible(
+                        N=self.Cout, groups=gn_groups, rows_per_sample=Ho * Wo, residual=residual):
+                    gn = rt.gn_site(x.n, gn_groups)
+                ops.gemm(cols, self.w.get(), out, tc=True, gn=gn, **kw)
+                return FMap(out, x.n, Ho, Wo, self.Cout, gn)
             else:
                 a = src.t
                 if a.dtype != rt.act_dtype:
                     a = rt.empty(src.M, src.C)
                     ops.cast2d(src.t, src.C, a, src.C, rows=src.M, cols=src.C)
-                ops.gemm(a, self.w.get(), out, conv=dict(n_img=x.n, H=H, W=W, Cin=self.Cin), tc=True, **kw)
+                cv = dict(n_img=x.n, H=H, W=W, Cin=self.Cin)
+                gn = None
+                if gn_groups and rt.gn_fuse and act == ops.ACT_NONE and ops.gn_eligible(
+                        N=self.Cout, groups=gn_groups, rows_per_sample=Ho * Wo, conv=cv, residual=residual):
+                    gn = rt.gn_site(x.n, gn_groups)
+                ops.gemm(a, self.w.get(), out, conv=cv, tc=True, gn=gn, **kw)
+                return FMap(out, x.n, Ho, Wo, self.Cout, gn)
         return FMap(out, x.n, Ho, Wo, self.Cout)
 
 
@@ -319,8 +361,13 @@ class GroupNorm:
 
     def __call__(self, x: FMap, silu: bool) -> FMap:
         out = self.rt.empty(x.M, x.C)
-        ops.groupnorm(x.t, self.g, self.b, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups, eps=self.eps, silu=silu,
-                      scratch_owner=id(self.rt))
+        if x.gn is not None and tuple(x.gn.shape) == (x.n, self.groups, 2):
+            # the producer of x accumulated the statistics in its epilogue: one pass over x (opt-in path)
+            ops.groupnorm_apply_sums(x.t, self.g, self.b, x.gn, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups,
+                                     eps=self.eps, silu=silu)
+        else:
+            ops.groupnorm(x.t, self.g, self.b, out, n_img=x.n, HW=x.H * x.W, C=x.C, groups=self.groups, eps=self.eps,
+                          silu=silu, scratch_owner=id(self.rt))
         return FMap(out, x.n, x.H, x.W, x.C)
 
 
@@ -354,7 +401,8 @@ class ResnetBlock2D:
     def __call__(self, x: FMap, temb_act: torch.Tensor) -> FMap:
         """x: fp32 stream (or act-dtype concat); temb_act = silu(emb) [n, T] fp32."""
         rt = self.rt
-        h = self.conv1(self.norm1(x, silu=True), rowvec=self.time_emb_proj(temb_act))
+        G = self.norm2.groups
+        h = self.conv1(self.norm1(x, silu=True), rowvec=self.time_emb_proj(temb_act), gn_groups=G)
         h = self.norm2(h, silu=True)
         if self.conv_shortcut is not None:
             a = x.t
@@ -364,7 +412,10 @@ class ResnetBlock2D:
             res = self.conv_shortcut(a, x.M, out_dtype=torch.float32)
         else:
             res = x.t
-        return self.conv2(h, out_dtype=torch.float32, residual=res)
+        # the block output is normalised next by a GroupNorm of the same group count (the next resnet's norm1, the
+        # Transformer2DModel's norm, conv_norm_out) unless it goes into a concat first: offering the statistics costs a
+        # few shuffles per epilogue chunk
+        return self.conv2(h, out_dtype=torch.float32, residual=res, gn_groups=G)
 
 
 class _ShortcutSrc:
@@ -392,8 +443,8 @@ class Downsample2D:
     def __init__(self, rt, src, p):
         self.conv = Conv3x3(rt, src, p + ".conv", stride=2)
 
-    def __call__(self, x: FMap) -> FMap:
-        return self.conv(x, out_dtype=torch.float32)
+    def __call__(self, x: FMap, gn_groups: int = 0) -> FMap:
+        return self.conv(x, out_dtype=torch.float32, gn_groups=gn_groups)
 
 
 class Upsample2D:

@@ -7,6 +7,7 @@ failure.  Nothing in this module computes with torch ops.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -166,13 +167,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          residual=None, ld_res: Optional[int] = None, aux=None, ld_aux: Optional[int] = None,
          ld_out: Optional[int] = None, act: int = ACT_NONE, pair: int = PAIR_NONE,
          bn: Optional[int] = None, conv: Optional[dict] = None, tc: bool = True,
-         cluster: Optional[int] = None, ln_out=None, ln_in=None):
+         cluster: Optional[int] = None, ln_out=None, ln_in=None, gn=None):
     """out = epilogue(A · Wᵀ).  conv = dict(n_img, H, W, Cin, stride=1, up2=0) for 3x3 pad-1.
 
     Folded LayerNorm (tc only, include/instantir_b200.h): ``ln_out`` = object with ``.acc`` ([2, M, 2] int64: two
     alternating row-sum accumulators, zero-initialised), ``.cur`` (index of the live one) and ``.h16`` ([M, N]
     16-bit): this GEMM adds the sums of its rows into ``acc[cur]`` and writes ``h16`` next to ``out``.  ``ln_in`` =
-    (such an object, colsum [N] fp32, eps): A must be its ``.h16``; clears ``acc[cur ^ 1]`` and flips ``cur``."""
+    (such an object, colsum [N] fp32, eps): A must be its ``.h16``; clears ``acc[cur ^ 1]`` and flips ``cur``.
+
+    GroupNorm statistics from the epilogue (tc only, opt-in): ``gn`` = zeroed int64 tensor [n_samples, groups, 2]; the launch
+    adds the fixed-point (sum, sum of squares) of its final output values per (sample, group) into it
+    (iir_gemm_args.gn_sums; consumer: ``groupnorm_apply_sums``).  ``gn_eligible`` tells whether a launch qualifies."""
     lib = _L(a, w, out)
     n_out = N // 2 if pair else N
     g = _lib.GemmArgs()
@@ -214,12 +219,52 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         g.ln_stats_in, g.ln_stats_zero = _p(st.acc[st.cur]), _p(st.acc[st.cur ^ 1])
         g.ln_colsum, g.ln_eps = _p(_f32c(colsum, "ln colsum")), eps
         st.cur ^= 1  # the next producer adds into the accumulator this launch clears
+    if gn is not None:
+        if gn.dtype != torch.int64 or not gn.is_contiguous() or gn.ndim != 3 or gn.shape[2] != 2 or N % gn.shape[1]:
+            raise TypeError("gn must be a contiguous int64 [n_samples, groups, 2] tensor with N % groups == 0")
+        g.gn_sums, g.gn_groups, g.gn_cpg = _p(gn), gn.shape[1], N // gn.shape[1]
     fn = lib.iir_gemm_tc if tc else lib.iir_gemm_simt
     name = ("conv3x3_" if conv is not None else "gemm_") + ("tc" if tc else "simt")
     with _Prof(name, flops=2.0 * M * N * K, M=M, N=N, K=K, pair=int(pair), key=key, epi=epi,
                conv=None if conv is None else (conv["n_img"], conv["H"], conv["W"], conv["Cin"])):
         _lib.check(fn(C.byref(g), _stream()), "iir_gemm_tc" if tc else "iir_gemm_simt", lib)
     return out
+
+
+def gn_eligible(*, N: int, groups: int, rows_per_sample: int, conv: Optional[dict] = None, residual=None, pair: int = PAIR_NONE) -> bool:
+    """can this tcgen05 launch accumulate GroupNorm statistics in its epilogue?  Mirrors the checks of iir_gemm_tc
+    (plain epilogue on the direct-store path, even channels per group, the 32 rows of a warp inside one sample)."""
+    if pair != PAIR_NONE or groups <= 0 or N % groups or (N // groups) % 2:
+        return False
+    if residual is not None and residual.dtype != torch.float32:
+        return False
+    if os.environ.get("IIR_GEMM_DIRECT", "2") != "2" or os.environ.get("IIR_GEMM_CLUSTER", "0") not in ("0", "1", "22"):
+        return False
+    if conv is not None:
+        return conv.get("stride", 1) == 1 and conv["W"] % 8 == 0 and conv["H"] >= 4
+    return rows_per_sample > 0 and rows_per_sample % 32 == 0
+
+
+def groupnorm_apply_sums(x, gamma, beta, sums, out, *, n_img: int, HW: int, C: int, groups: int = 32, eps: float = 1e-5,
+                         silu: bool = False):
+    """GroupNorm's second half alone: (mean, rstd) come from the fixed-point sums the PRODUCER of x accumulated (gemm(gn=...))"""
+    lib = _L(x, out)
+    if sums.dtype != torch.int64 or not sums.is_contiguous() or tuple(sums.shape) != (n_img, groups, 2):
+        raise TypeError("sums must be the contiguous int64 [n_img, groups, 2] tensor the producing GEMM accumulated into")
+    with _Prof("groupnorm_apply", bytes=float(n_img) * HW * C * (x.element_size() + out.element_size())):
+        _lib.check(lib.iir_groupnorm_apply_sums(_p(x), _dt(x), _p(_f32c(gamma, "gamma")), _p(_f32c(beta, "beta")), _p(sums),
+                                                _p(out), _dt(out), n_img, HW, C, groups, eps, int(silu), _stream()),
+                   "iir_groupnorm_apply_sums", lib)
+    return out
+
+
+def memset_zero(t: torch.Tensor):
+    """cudaMemsetAsync on the current stream (a memset node inside a captured forward)"""
+    lib = _L(t)
+    if not t.is_contiguous():
+        raise TypeError("memset_zero needs a contiguous tensor")
+    _lib.check(lib.iir_memset_zero(_p(t), t.numel() * t.element_size(), _stream()), "iir_memset_zero", lib)
+    return t
 
 
 def conv3x3_direct(x, w, bias, out, *, in_nchw: bool, out_nchw: bool, n_img: int, H: int, W: int,

@@ -120,8 +120,13 @@ class Transformer2DModel:
         y = h
         for k, blk in enumerate(self.transformer_blocks):
             y = blk(h, x.n, n_tok, encoder_hidden_states, kw, last=k == len(self.transformer_blocks) - 1)
-        out = self.proj_out(y, x.M, out_dtype=torch.float32, residual=x.t)
-        return FMap(out, x.n, x.H, x.W, x.C)
+        # opt-in (IIR_GN_FUSE): the block output is normalised next by a GroupNorm of the same group count (the next
+        # resnet's norm1) unless a concat comes first — its statistics ride on this epilogue
+        gn = None
+        if self.rt.gn_fuse and ops.gn_eligible(N=self.C, groups=self.norm.groups, rows_per_sample=n_tok, residual=x.t):
+            gn = self.rt.gn_site(x.n, self.norm.groups)
+        out = self.proj_out(y, x.M, out_dtype=torch.float32, residual=x.t, gn=gn, rows_per_sample=n_tok if gn is not None else 0)
+        return FMap(out, x.n, x.H, x.W, x.C, gn)
 
 
 class DownBlock:
@@ -140,7 +145,7 @@ class DownBlock:
                 x = self.attentions[j](x, ehs, kw)
             outs.append(x)
         if self.downsamplers is not None:
-            x = self.downsamplers[0](x)
+            x = self.downsamplers[0](x, gn_groups=self.resnets[0].norm1.groups)  # the next block's norm1 reads it
             outs.append(x)
         return x, outs
 

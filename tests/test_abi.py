@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
 
     fields_g = ["a", "M", "lda", "conv", "bias", "rows_per_sample", "residual", "ld_res", "aux", "out",
-                "ld_out", "act", "bn", "cluster", "ld_rowvec"]
+                "ld_out", "act", "bn", "cluster", "ld_rowvec", "ln_eps", "conv_asym", "gn_sums", "gn_cpg", "gn_groups"]
     fields_a = ["q", "n_seg", "k", "ldk", "k_off", "v", "kv_len", "seg_scale", "out", "dtype", "n_q",
                 "softmax_scale"]
     prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "instantir_b200.h"', "int main(void){",

@@ -253,6 +253,7 @@ gn_apply_sums_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, 
                      const long long* __restrict__ sums, TO* __restrict__ out, int HW, int C, int groups, double inv_count,
                      float eps, int silu, int rows_per_block, int TX, int TY) {
   extern __shared__ float sm[];  // [C] scale, [C] shift
+  __shared__ float s_mean[64], s_rstd[64];  // groups <= 64 (checked on the host)
   pdl_trigger();
   pdl_wait();
   float* s_scale = sm;
@@ -260,15 +261,19 @@ gn_apply_sums_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, 
   const int img = blockIdx.y;
   const int cpg = C / groups;
   const long long* s_sums = sums + static_cast<long long>(img) * groups * 2;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {  // one fp64 finalisation per group and block
     const double mean = static_cast<double>(__ldcg(s_sums + 2 * g)) * (1.0 / GN_S1_SCALE) * inv_count;
     double var = static_cast<double>(__ldcg(s_sums + 2 * g + 1)) * (1.0 / GN_S2_SCALE) * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = rstd * (gamma ? gamma[c] : 1.0f);
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * (gamma ? gamma[c] : 1.0f);
     s_scale[c] = sc;
-    s_shift[c] = (beta ? beta[c] : 0.0f) - static_cast<float>(mean) * sc;
+    s_shift[c] = (beta ? beta[c] : 0.0f) - s_mean[g] * sc;
   }
   __syncthreads();
   gn_apply_rows<TI, TO>(x, out, s_scale, s_shift, HW, C, silu, rows_per_block, TX, TY);

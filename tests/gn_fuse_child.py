@@ -1,4 +1,4 @@
-"""Child process of tests/test_gn_fuse_gpu.py and of bench.py's `experimental_gn_fuse` leg: exercises the OPT-IN fused
+"""Child process of tests/test_zz_gn_fuse_gpu.py and of bench.py's `experimental_gn_fuse` leg: exercises the OPT-IN fused
 GroupNorm path (IIR_GN_FUSE=1: statistics accumulated by the producing GEMM / conv epilogue, iir_groupnorm_apply_sums) in a
 process of its own, so that a fault in that not-yet-GPU-verified path cannot poison the CUDA context of the caller.
 

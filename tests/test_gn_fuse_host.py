@@ -2,7 +2,7 @@
 producers (ResnetBlock2D.conv1 / conv2, the stride-2 downsampler GEMM) and the consumer (GroupNorm.__call__), with the C-ABI
 calls of instantir_b200.ops replaced by torch emulations that follow the kernels' contracts (fixed-point sums included).  It
 checks the plumbing — which statistics reach which GroupNorm, fall-backs, arena reuse across forwards — not the kernels
-(those run in tests/test_gn_fuse_gpu.py on the driver's GPU)."""
+(those run in tests/test_zz_gn_fuse_gpu.py on the driver's GPU)."""
 import torch
 import torch.nn.functional as F
 

@@ -195,3 +195,44 @@ def test_partition_deadline_prints_the_line_and_leaves(stubbed_bench, monkeypatc
     first = lines[0]
     assert "partitions_aborted" in first and first["partitions"] == {} and first["value"] > 0 and first["n_gpus"] == 2
     time.sleep(0.05)
+
+
+def test_two_rank_run_records_the_communicating_partitions(stubbed_bench, monkeypatch):
+    """WORLD_SIZE=2 with stubbed collectives: the main line carries the config-3 CFG-parallel and data-parallel sub-records and
+    the deadline timer is cancelled"""
+    import threading
+
+    import torch.distributed as dist
+
+    bench, lines = stubbed_bench
+    from instantir_b200 import parallel
+
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    for name in ("init_process_group", "barrier", "destroy_process_group"):
+        monkeypatch.setattr(dist, name, lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
+    monkeypatch.setattr(parallel, "CFGParallel", lambda: types.SimpleNamespace(branch=0))
+    monkeypatch.setattr(torch, "tensor", lambda data, device=None, dtype=None: torch.as_tensor(data, dtype=dtype))
+    timers = []
+    real_timer = threading.Timer
+
+    def make_timer(secs, fn):
+        t = real_timer(secs, fn)
+        timers.append((secs, t))
+        return t
+
+    monkeypatch.setattr(threading, "Timer", make_timer)
+    monkeypatch.setattr(os, "_exit", lambda code: (_ for _ in ()).throw(AssertionError("the deadline fired in a healthy run")))
+    bench.run_ours(_args(bench))
+    (secs, t), = timers
+    assert secs >= 90.0 and t.finished.is_set() or not t.is_alive()  # cancelled
+    line, = lines
+    assert line["n_gpus"] == 2 and "partitions_aborted" not in line
+    parts = line["partitions"]
+    assert set(parts) == {"config3_cfg_parallel", "config3_data_parallel"}
+    for rec in parts.values():
+        assert rec["value"] > 0 and rec["ms_per_step"] > 0 and "error" not in rec
+    assert parts["config3_cfg_parallel"]["images"] == 1 and parts["config3_data_parallel"]["images"] == 2
+    assert "experimental_gn_fuse" not in line  # N = 1 only

@@ -190,3 +190,35 @@ def test_arena_exhaustion_and_ineligible_shapes_fall_back(monkeypatch):
     assert not ops.gn_eligible(N=96, groups=32, rows_per_sample=1024)                                    # 3 channels per group: odd
     assert not ops.gn_eligible(N=320, groups=32, rows_per_sample=64, conv=dict(n_img=1, H=2, W=32, Cin=64))  # < 4 rows
     assert ops.gn_eligible(N=320, groups=32, rows_per_sample=64, conv=dict(n_img=1, H=8, W=8, Cin=64))
+
+
+def test_the_gpu_child_script_itself_is_sound(monkeypatch):
+    """tests/gn_fuse_child.py (the kernel checks the driver's GPU run will execute) against the torch emulations: a Python slip
+    in the checker must not make a correct kernel look broken — reference computations, shapes, tolerances and the expected
+    rejection of an ineligible launch are exercised here on the CPU."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("gn_fuse_child", os.path.join(os.path.dirname(os.path.abspath(__file__)), "gn_fuse_child.py"))
+    child = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(child)
+    fake = _Fake()
+
+    def gemm(a, w, out, **kw):
+        gn, conv = kw.get("gn"), kw.get("conv")
+        if gn is not None and not ops.gn_eligible(N=kw["N"], groups=gn.shape[1], rows_per_sample=kw.get("rows_per_sample", 0), conv=conv,
+                                                  residual=kw.get("residual")):
+            raise ops._lib.IIRError("iir_gemm_tc failed (-1): gn_sums needs rows_per_sample % 32 == 0")  # what the C side answers
+        return fake.gemm(a, w, out, **kw)
+
+    monkeypatch.setattr(child, "DEV", "cpu")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    for name in ("groupnorm", "groupnorm_apply_sums", "memset_zero"):
+        monkeypatch.setattr(ops, name, getattr(fake, name))
+    monkeypatch.setattr(ops, "gemm", gemm)
+    checks = {}
+    child.run_kernels(checks)
+    assert any(k.endswith(":rejected") for k in checks)
+    sums = [v for k, v in checks.items() if k.endswith(":sumsq_rel_err")]
+    assert len(sums) >= 12 and max(sums) < 1e-5          # the emulation is exact up to fixed-point rounding
+    assert max(v for k, v in checks.items() if "_vs_two_kernel" in k) < 2e-3

@@ -350,8 +350,9 @@ def test_guidance_rescale_fp32():
 ADASTEP_UNVERIFIED = ("row f4 (adastep_restore) is NOT re-verified on a GPU: the only GPU run of this test (round 2, before the commit "
                       "that introduced it) failed on preview_factor at the first previewing step; the host loop was changed afterwards "
                       "(loop.last_previewed in instantir_b200/pipeline.py: pred_x0 is compared with the last preview latent the "
-                      "Aggregator was fed, not with the LQ latent), but the round's GPU budget was spent before the test could run "
-                      "again.  Non-strict: an XPASS in the driver's log is the verification.")
+                      "Aggregator was fed, not with the LQ latent) and now reproduces the oracle's bookkeeping on the CPU "
+                      "(tests/test_pipeline_loop_cpu.py::test_adastep_restore_bookkeeping_matches_oracle), but the round's GPU budget was "
+                      "spent before this test could run again.  Non-strict: an XPASS in the driver's log is the GPU verification.")
 
 
 @pytest.mark.xfail(reason=ADASTEP_UNVERIFIED, strict=False)

@@ -77,8 +77,8 @@ def test_aggregator_vs_reference_forward_vector(precision):
 
 
 NOT_YET_RUN_ON_GPU = ("written after the round's GPU budget was spent: the code under test is exercised on the CPU only "
-                      "(tests/test_host_logic.py covers its weight source and validation); non-strict, so an XPASS in the driver's "
-                      "log is the GPU verification")
+                      "(tests/test_host_logic.py covers its weight source and validation, tests/test_model_host_cpu.py runs the same "
+                      "scenario with emulated kernels); non-strict, so an XPASS in the driver's log is the GPU verification")
 
 
 @pytest.mark.xfail(reason=NOT_YET_RUN_ON_GPU, strict=False)

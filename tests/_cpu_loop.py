@@ -8,6 +8,19 @@ from instantir_b200 import ops
 from oracle import pipeline as opipe
 
 
+class NullStream:
+    """stand-in for torch.cuda.Stream on a box without a GPU: work runs in program order"""
+
+    def __init__(self, device=None):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+
 class OracleUNet:
     """oracle UNet behind the product UNet's call surface (unet.py: forward(..., additional_residual_scale=))"""
 
@@ -91,4 +104,4 @@ def emulate_ops(setattr_fn):
     for name, fn in dict(step_prologue=step_prologue, lcm_step=lcm_step, cfg_ddpm_step=cfg_ddpm_step, add_noise=add_noise,
                          adastep_update=adastep_update, cfg_rescale=cfg_rescale).items():
         setattr_fn(ops, name, fn)
-    setattr_fn(torch.cuda, "Stream", lambda device=None: SimpleNamespace())
+    setattr_fn(torch.cuda, "Stream", NullStream)

@@ -280,6 +280,8 @@ def install(setattr_fn, fuse_gn=False):
         self.gn_fuse = bool(fuse_gn) and self.tc
 
     setattr_fn(nn.Runtime, "__init__", init)
-    setattr_fn(torch.cuda, "Stream", lambda device=None: None)
+    from _cpu_loop import NullStream
+
+    setattr_fn(torch.cuda, "Stream", NullStream)
     os.environ.pop("IIR_GN_FUSE", None)
     return emu

@@ -18,7 +18,7 @@ from oracle import pipeline as opipe
 from oracle import schedulers as osched
 
 
-def _oracle_and_product(monkeypatch, precision, fuse_gn=False, B=1, lat=16, steps=2, **kw):
+def _oracle_and_product(monkeypatch, precision, fuse_gn=False, B=1, lat=16, steps=2, overlap=False, **kw):
     from instantir_b200.aggregator import Aggregator
     from instantir_b200.unet import UNet2DConditionModel
 
@@ -46,7 +46,7 @@ def _oracle_and_product(monkeypatch, precision, fuse_gn=False, B=1, lat=16, step
                pooled_prompt_embeds=inp["pooled_prompt_embeds"], negative_pooled_prompt_embeds=inp["negative_pooled_prompt_embeds"],
                ip_adapter_image_embeds=[inp["ip"]], num_inference_steps=steps, guidance_scale=7.0,
                previewer_scheduler=schedulers.LCMSingleStepScheduler(), generator=torch.Generator().manual_seed(42),
-               use_cuda_graph=False, overlap_streams=False, record=rec_p, **kw)
+               use_cuda_graph=False, overlap_streams=overlap, record=rec_p, **kw)
     return ref, rec_o, out.images, rec_p, emu
 
 
@@ -129,3 +129,29 @@ def test_aggregator_from_unet_and_load_state_dict_host_code(monkeypatch):
     assert res.missing_keys and all(k.startswith("controlnet_mid_block") for k in res.missing_keys)
     _, mid2 = agg(inp["image"], t, None, **kw)
     assert torch.equal(mid2, mid)
+
+
+class _Ev:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+
+@pytest.mark.parametrize("fuse_gn", [False, True])
+def test_forked_step_host_code_matches_oracle(monkeypatch, fuse_gn):
+    """the DEFAULT step schedule (overlap_streams=True: UNet down + mid on a second stream beside the Aggregator, SFT heads on
+    that stream too, then the up path) — with streams stubbed to run in program order, the host code must still reproduce
+    the oracle; also with the opt-in fused GroupNorm (separate accumulator arenas per model)"""
+    import contextlib
+
+    from _cpu_loop import NullStream
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: NullStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", _Ev)
+    ref, rec_o, out, rec_p, emu = _oracle_and_product(monkeypatch, "fp16", fuse_gn=fuse_gn, steps=2, overlap=True, preview_start=0.5)
+    assert len(rec_p["latents"]) == 2
+    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+        assert rel_l2(a, b) < 1e-2, f"step {i}: {rel_l2(a, b):.3e}"

@@ -64,3 +64,26 @@ def test_invalid_arguments_are_reported_not_crashed():
     g.a_dtype = g.w_dtype = _lib.F32
     assert lib.iir_gemm_tc(ctypes.byref(g), None) == -1  # fp32 operands are refused by the tc path
     assert b"bf16" in lib.iir_last_error()
+
+
+def test_opt_in_groupnorm_entry_points_validate_their_arguments():
+    """ABI 11: argument checks answer with a status and a message, on a box without a GPU too"""
+    lib = _lib.load()
+    assert lib.iir_memset_zero(None, 16, None) == -1 and b"iir_memset_zero" in lib.iir_last_error()
+    assert lib.iir_groupnorm_apply_sums(None, 0, None, None, None, None, 0, 1, 64, 64, 32, 1e-5, 0, None) == -1
+    assert b"iir_groupnorm_apply_sums" in lib.iir_last_error()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf) + (-ctypes.addressof(buf)) % 256  # an aligned, non-null address: every call below is refused before a launch
+    assert lib.iir_groupnorm_apply_sums(p, 0, None, None, p, p, 0, 1, 64, 100, 32, 1e-5, 0, None) == -1  # C % groups != 0
+    g = _lib.GemmArgs()
+    g.a = g.w = g.out = p
+    g.a_dtype = g.w_dtype = g.out_dtype = lib.iir_h16_dtype()
+    g.M, g.N, g.K, g.lda, g.ld_out, g.bn = 256, 320, 64, 64, 320, 160
+    g.gn_sums, g.gn_groups, g.gn_cpg = p, 32, 10
+    g.rows_per_sample = 100                      # a warp's 32 rows would straddle two samples
+    rc = lib.iir_gemm_tc(ctypes.byref(g), None)
+    assert rc != 0
+    msg = lib.iir_last_error()
+    assert b"rows_per_sample" in msg or b"cuTensorMapEncodeTiled" in msg or b"CUDA" in msg, msg
+    g.gn_cpg = 9                                 # odd group width / N != groups * cpg
+    assert lib.iir_gemm_tc(ctypes.byref(g), None) != 0

@@ -275,7 +275,8 @@ def experimental_gn_fuse(args, line):
     against this run's default path."""
     import math
 
-    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(args.warmup), "--precision",
+    # 10 timed steps are enough for a step time; the latents fingerprint is taken after the first warm-up step either way
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(min(args.steps, 10)), "--warmup", str(args.warmup), "--precision",
            args.precision, "--no-cpu", "--no-alt", "--no-vae", "--no-experimental"]
     env = dict(os.environ, IIR_GN_FUSE="1")
     t0 = time.perf_counter()

@@ -261,7 +261,43 @@ class Emulation:
         out.copy_(torch.cat([torch.cos(arg), torch.sin(arg)], 1).to(out.dtype))
         return out
 
-    NAMES = ("gemm", "conv3x3_direct", "linear_small", "attention", "groupnorm", "groupnorm_apply_sums", "memset_zero", "layernorm",
+    # ---------------------------------------------------------------------------------------------- rows f1 / f2
+    def softmax_rows(self, x, out, *, scale):
+        self.calls.append(("softmax_rows", {}))
+        out.copy_(torch.softmax(x.float() * scale, -1).to(out.dtype))
+        return out
+
+    def gaussian_sample(self, moments, noise, out, *, scale=1.0):
+        self.calls.append(("gaussian_sample", {}))
+        mean, logvar = moments.float().chunk(2, dim=1)
+        std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+        out.copy_((mean + (std * noise if noise is not None else 0.0)) * scale)
+        return out
+
+    def embed_tokens(self, ids, token_embedding, position_embedding, out, *, seq_len):
+        self.calls.append(("embed_tokens", {}))
+        r = torch.arange(ids.numel())
+        out.reshape(ids.numel(), -1).copy_(token_embedding[ids.reshape(-1)] + position_embedding[r % seq_len])
+        return out
+
+    def patchify(self, img, out, *, patch):
+        self.calls.append(("patchify", {}))
+        n, c, h, w = img.shape
+        cols = F.unfold(img.float(), patch, stride=patch)          # [n, c*p*p, gh*gw], (c, ky, kx) order
+        rows = cols.transpose(1, 2).reshape(-1, c * patch * patch)
+        out.zero_()
+        out[:, :rows.shape[1]].copy_(rows.to(out.dtype))
+        return out
+
+    def vit_assemble(self, patches, cls, pos, out, *, n_img, P):
+        self.calls.append(("vit_assemble", {}))
+        D = patches.shape[-1]
+        o = out.reshape(n_img, P + 1, D)
+        o[:, 0] = cls.reshape(1, D) + pos.reshape(P + 1, D)[0]
+        o[:, 1:] = patches.reshape(n_img, P, D) + pos.reshape(P + 1, D)[1:]
+        return out
+
+    NAMES = ("softmax_rows", "gaussian_sample", "embed_tokens", "patchify", "vit_assemble", "gemm", "conv3x3_direct", "linear_small", "attention", "groupnorm", "groupnorm_apply_sums", "memset_zero", "layernorm",
              "adaln_items", "adaln_batched", "concat_inject", "upsample2x", "im2col3x3_s2", "cast2d", "silu", "add", "scale",
              "timestep_embedding")
 

@@ -281,9 +281,11 @@ class InstantIRPipeline:
 
                 src_img = dinov2_preprocess((image.float() + 1.0) / 2.0)
             ip_adapter_image_embeds = self.prepare_ip_adapter_image_embeds(src_img, None, None, num_images_per_prompt, True)
-        if multistep_restore or denoising_end or reference_latents is not None:
-            raise NotImplementedError("multistep_restore (calls scheduler.step with kwargs stock DDPM does not have: not runnable in the "
-                                      "reference as shipped, SURVEY App. E) / denoising_end / reference_latents are not built (SURVEY §8 f4)")
+        if multistep_restore:
+            raise NotImplementedError("multistep_restore calls scheduler.step with kwargs stock DDPM does not have: not runnable in the "
+                                      "reference as shipped (SURVEY App. E, §8 f4)")
+        if reference_latents is not None and agg_ahead:
+            raise NotImplementedError("reference_latents with agg_ahead: the one-step-ahead Aggregator is fed the LQ latent")
         if adastep_restore and (cfg_parallel is not None or agg_ahead):
             raise NotImplementedError("adastep_restore with cfg_parallel / agg_ahead: the adaptive factor lives on the cond rank and "
                                       "makes the Aggregator's schedule data dependent")
@@ -323,6 +325,13 @@ class InstantIRPipeline:
         H_px, W_px = h * 8, w * 8
         ts, num_inference_steps = retrieve_timesteps(sched, num_inference_steps, dev, timesteps)
         n = len(ts)
+        n_run = n
+        if denoising_end is not None and isinstance(denoising_end, float) and 0 < denoising_end < 1:
+            # 8.1 (:1469-1484): only the timesteps at or above the cut-off run; controlnet_keep / previewing (:1415-1421) and
+            # the scheduler keep the FULL schedule
+            n_train = sched.config.num_train_timesteps
+            cutoff = int(round(n_train - denoising_end * n_train))
+            n_run = len([t for t in torch.as_tensor(ts).tolist() if t >= cutoff])
         # 6. latents (:1388-1401): the LQ latent noised to t0 with the user's generator (init_latents :931-939; a passed
         # `latents` is ignored on this branch, as in the reference), else prepare_latents (:942-963)
         if init_latents_with_lq:
@@ -372,6 +381,13 @@ class InstantIRPipeline:
             time_ids_all=time_ids.repeat(len(branches), 1),
             image_all=torch.cat([image] * len(branches), 0),
             ip_all=torch.cat([ip[b] for b in branches], 0).unsqueeze(1))
+        ref_given = reference_latents is not None
+        if ref_given:
+            # :1579-1580: on controlled steps that do not preview, the Aggregator is fed this latent instead of the LQ one
+            ref = reference_latents.to(**f32).contiguous()
+            if tuple(ref.shape) != tuple(image.shape):
+                raise ValueError(f"reference_latents must have the LQ latent's shape {tuple(image.shape)}, got {tuple(ref.shape)}")
+            new["ref_all"] = torch.cat([ref] * len(branches), 0)
         # Static tensors + captured graphs are kept across calls of the same shape: new conditioning is
         # copied INTO the static buffers (version bump -> step-invariant caches recompute in place), so the
         # graphs captured for the first image are replayed for every later one.
@@ -497,6 +513,11 @@ class InstantIRPipeline:
             S.g_unet_res = {"prev": _Graphed(f_unet(True), use_cuda_graph), "lq": _Graphed(f_unet(True), use_cuda_graph),
                             "buf0": _Graphed(f_unet_buf(0), use_cuda_graph), "buf1": _Graphed(f_unet_buf(1), use_cuda_graph)}
             S.g_unet_plain = _Graphed(f_unet(False), use_cuda_graph)
+            S.g_agg_ref = None
+            if ref_given:
+                S.g_step["ref"] = _Graphed(f_step(S.ref_all), use_cuda_graph)
+                S.g_agg_ref = _Graphed(f_agg(S.ref_all), use_cuda_graph)
+                S.g_unet_res["ref"] = _Graphed(f_unet(True), use_cuda_graph)
         else:
             for k, v in new.items():
                 getattr(S, k).copy_(v)
@@ -509,8 +530,8 @@ class InstantIRPipeline:
             S.previewer_mean.zero_()
             S.preview_factor.fill_(1.0)
             S.cond_scale.fill_(min(1.0, float(scales[0])) * keep[0])
-        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n, timesteps=ts, ahead=None, last_previewed=False)
-        ahead_ok = g_step is not None and agg_ahead
+        loop = SimpleNamespace(latents=latents, res_src=None, preview_row=[], n_steps=n_run, timesteps=ts, ahead=None, last_previewed=False)
+        ahead_ok = g_step is not None and agg_ahead and not ref_given
 
         def lq_step(j):
             """step j runs the Aggregator on the LQ latent alone (no preview): its output depends only on t_j"""
@@ -544,7 +565,7 @@ class InstantIRPipeline:
                         loop.preview_row.append(preview_latent[-B:].clone())
                     loop.res_src = "prev"
                 else:
-                    loop.res_src = "lq"
+                    loop.res_src = "ref" if ref_given else "lq"
                     loop.last_previewed = False
                 if not previewed and ahead_ok:
                     # Aggregator(t_i) was computed beside the UNet of step i-1 (or is computed now, once per run);
@@ -567,7 +588,7 @@ class InstantIRPipeline:
                     loop.ahead = None
                     noise_pred, st.down, st.mid = g_step[loop.res_src]()   # aggregator || UNet down+mid, then UNet up
                 else:
-                    st.down, st.mid = (g_agg_prev if previewed else g_agg_lq)()
+                    st.down, st.mid = {"prev": g_agg_prev, "lq": g_agg_lq, "ref": S.g_agg_ref}[loop.res_src]()
             if noise_pred is not None:
                 pass
             elif st.down is None:
@@ -598,7 +619,7 @@ class InstantIRPipeline:
                 # the Aggregator was fed (the LQ latent on non-previewing steps)
                 if loop.res_src is None:
                     raise RuntimeError("adastep_restore before any controlled step (the reference raises NameError here)")
-                pv = preview_latent[-B:] if loop.last_previewed else S.image_all[-B:]
+                pv = preview_latent[-B:] if loop.last_previewed else (S.ref_all if ref_given else S.image_all)[-B:]
                 nxt = i + 1 if i + 1 < n else i
                 ops.adastep_update(pv, out.pred_original_sample, S.previewer_mean, S.preview_factor, cond_scale, n_rep=len(branches),
                                    next_scale=float(scales[nxt]), next_keep=keep[nxt])
@@ -619,7 +640,7 @@ class InstantIRPipeline:
         if bad:  # check_inputs, :774-779
             raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but found {bad}")
         nbr = len(branches)
-        for i in range(n):
+        for i in range(n_run):
             step(i)
             if callback_on_step_end is not None:
                 # :1650-1658.  Inside the reference's loop `prompt_embeds` is the CFG-concatenated tensor the UNet reads;

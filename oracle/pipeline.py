@@ -37,7 +37,8 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                     preview_start=0.0, preview_end=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
                     controlnet_conditioning_scale=1.0, generator=None, init_latents_with_lq=True,
                     timesteps=None, record: Optional[dict] = None, guidance_rescale: float = 0.0,
-                    max_steps: Optional[int] = None, adastep_restore: bool = False):
+                    max_steps: Optional[int] = None, adastep_restore: bool = False, denoising_end: Optional[float] = None,
+                    reference_latents=None):
     """Returns the final latents [B,4,h,w]; `record` (if given) collects per-step tensors.
 
     image: LQ latent [B,4,h,w] (the reference accepts 4-channel tensors as latents, :1370-1382).
@@ -55,6 +56,10 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
         latents = torch.randn(image.shape, generator=generator, dtype=image.dtype) * scheduler.init_noise_sigma
     keep, previewing = step_masks(n, preview_start, preview_end, control_guidance_start, control_guidance_end)
     scales = controlnet_conditioning_scale if isinstance(controlnet_conditioning_scale, list) else [controlnet_conditioning_scale] * n
+    if denoising_end is not None and isinstance(denoising_end, float) and 0 < denoising_end < 1:  # 8.1, :1469-1484
+        n_train = scheduler.config.num_train_timesteps
+        cutoff = int(round(n_train - denoising_end * n_train))
+        ts = ts[: len([t for t in ts.tolist() if t >= cutoff])]
     add_text_embeds = pooled_prompt_embeds
     time_ids = add_time_ids
     if do_cfg:
@@ -89,6 +94,8 @@ def restore_latents(unet, aggregator, scheduler, previewer_scheduler, *, image, 
                 preview_latent = previewer_scheduler.step(preview_noise, t.to(dtype=torch.int64), x_in,
                                                           return_dict=False)[0]
                 unet.disable_adapters()
+            elif reference_latents is not None:  # :1579-1580
+                preview_latent = torch.cat([reference_latents] * 2) if do_cfg else reference_latents
             else:
                 preview_latent = image
             last_preview = preview_latent

@@ -200,6 +200,8 @@ def test_pipeline_rejects_out_of_scope_arguments():
         pipeline.InstantIRPipeline.__call__(p, prompt="a photo", prompt_embeds=torch.zeros(1, 77, 8))
     with pytest.raises(NotImplementedError):
         pipeline.InstantIRPipeline.__call__(p, multistep_restore=True)
+    with pytest.raises(NotImplementedError):
+        pipeline.InstantIRPipeline.__call__(p, reference_latents=torch.zeros(1, 4, 8, 8), agg_ahead=True)
 
 
 def test_from_unet_weight_source_matches_reference_from_unet():

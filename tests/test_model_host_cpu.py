@@ -155,3 +155,15 @@ def test_forked_step_host_code_matches_oracle(monkeypatch, fuse_gn):
     assert len(rec_p["latents"]) == 2
     for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
         assert rel_l2(a, b) < 1e-2, f"step {i}: {rel_l2(a, b):.3e}"
+
+
+def test_reference_latents_and_denoising_end_through_the_real_host_code(monkeypatch):
+    """the two options through the real UNet / Aggregator objects (emulated kernels): a third static conditioning buffer and
+    its own graph slots, a shortened run"""
+    refl = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(11))
+    ref, rec_o, out, rec_p, _ = _oracle_and_product(monkeypatch, "fp32", steps=4, preview_start=0.5, reference_latents=refl,
+                                                     denoising_end=0.75)
+    assert len(rec_p["latents"]) == len(rec_o["latents"]) == 3
+    for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
+        assert rel_l2(a, b) < 1e-4, f"step {i}: {rel_l2(a, b):.3e}"
+

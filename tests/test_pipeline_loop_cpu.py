@@ -88,3 +88,22 @@ def test_adastep_restore_bookkeeping_matches_oracle(monkeypatch, preview_start):
     for i, (a, b) in enumerate(zip(rec_p["latents"], rec_o["latents"])):
         assert rel_l2(a, b) < 1e-4, f"latents, step {i}"
     assert rel_l2(out.images, ref) < 1e-4
+
+
+def test_denoising_end_and_reference_latents_match_oracle(monkeypatch):
+    """denoising_end (pipelines/sdxl_instantir.py:1469-1484): only the timesteps at or above the cut-off run, while the step
+    masks keep the full schedule; reference_latents (:1579-1580): controlled steps that do not preview feed the Aggregator this
+    latent instead of the LQ one — also as the `preview` of adastep_restore"""
+    ref, rec_o, out, rec_p = _run(monkeypatch, steps=4, preview_start=0.0, denoising_end=0.5)
+    assert len(rec_o["latents"]) == len(rec_p["latents"]) == 2   # t = 751, 501 of [751, 501, 251, 1]; cut-off 500
+    _same_steps(rec_p, rec_o)
+    assert rel_l2(out.images, ref) < 2e-5
+    refl = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(11))
+    ref, rec_o, out, rec_p = _run(monkeypatch, B=2, steps=4, preview_start=0.5, reference_latents=refl)
+    _same_steps(rec_p, rec_o)
+    ref2, rec_o2, _, _ = _run(monkeypatch, B=2, steps=4, preview_start=0.5)
+    assert rel_l2(rec_o["latents"][0], rec_o2["latents"][0]) > 1e-3  # the option changes the result: the check is not vacuous
+    ref, rec_o, out, rec_p = _run(monkeypatch, B=2, steps=3, preview_start=1.0, reference_latents=refl, adastep_restore=True)
+    for a, b in zip(rec_p["preview_factor"], rec_o["preview_factor"]):
+        assert torch.equal(torch.isinf(a), torch.isinf(b)) and rel_l2(a[torch.isfinite(b)], b[torch.isfinite(b)]) < 1e-4
+    _same_steps(rec_p, rec_o, tol=1e-4)

@@ -25,7 +25,7 @@ emulate_ops(setattr)
 oc = ocfg.tiny()
 ounet, oagg = build_oracle(oc, seed=0, lora_alpha=8.0)
 B = 2
-inp = make_inputs(oc, B=B, h=16, w=16)
+inp = make_inputs(oc, B=B, h=8, w=8)
 common = dict(num_inference_steps=3, guidance_scale=7.0, preview_start=0.0)
 ref = opipe.restore_latents(
     ounet, oagg, osched.DDPMScheduler(), osched.LCMSingleStepScheduler(), image=inp["image"], prompt_embeds=inp["prompt_embeds"],

@@ -16,7 +16,7 @@ from oracle import pipeline as opipe
 from oracle import schedulers as osched
 
 
-def _run(monkeypatch, *, B=1, steps=3, guidance=7.0, lat=16, **kw):
+def _run(monkeypatch, *, B=1, steps=3, guidance=7.0, lat=8, **kw):
     emulate_ops(monkeypatch.setattr)
     oc = ocfg.tiny()
     ounet, oagg = build_oracle(oc, seed=0, lora_alpha=8.0)
@@ -98,7 +98,7 @@ def test_denoising_end_and_reference_latents_match_oracle(monkeypatch):
     assert len(rec_o["latents"]) == len(rec_p["latents"]) == 2   # t = 751, 501 of [751, 501, 251, 1]; cut-off 500
     _same_steps(rec_p, rec_o)
     assert rel_l2(out.images, ref) < 2e-5
-    refl = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(11))
+    refl = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(11))
     ref, rec_o, out, rec_p = _run(monkeypatch, B=2, steps=4, preview_start=0.5, reference_latents=refl)
     _same_steps(rec_p, rec_o)
     ref2, rec_o2, _, _ = _run(monkeypatch, B=2, steps=4, preview_start=0.5)
